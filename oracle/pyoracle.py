@@ -1,0 +1,292 @@
+"""ctypes bindings for the oracle -- TEST INFRASTRUCTURE ONLY.
+
+Two checkers live here:
+  * ``Oracle``    -- oracle/_build/libgnnoracle.so, the plain-C restatement
+                     (oracle/gnn_oracle.c), single-threaded; builds anywhere.
+  * ``Reference`` -- oracle/_ref/libgnnref.so, the UNMODIFIED reference forward
+                     (reference src/gnn_inference.cpp + src/matrix.cpp + OpenBLAS
+                     0.3.15), built in the container that has /root/reference.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import
+this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "_build" / "libgnnoracle.so"
+REF_SO = HERE / "_ref" / "libgnnref.so"
+REF_BIN = HERE / "_ref" / "GNN_VC_ref"
+REF_MODEL_INC = HERE / "_ref" / "model_text.inc"
+
+LINEAR, GRAPH, RELU, SIGMOID = 0, 1, 2, 3
+
+_f32p = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(ty) if a is not None else None
+
+
+def build_oracle(force: bool = False) -> Path:
+    """Compile the C restatement (gcc only; works on the GPU box too)."""
+    src = HERE / "gnn_oracle.c"
+    if force or not ORACLE_SO.exists() or ORACLE_SO.stat().st_mtime < src.stat().st_mtime:
+        subprocess.check_call(["make", "-s", "-C", str(HERE), "oracle"])
+    return ORACLE_SO
+
+
+def build_ref() -> Path | None:
+    """Compile the unmodified reference when /root/reference is present."""
+    if Path("/root/reference/src/gnn_inference.cpp").exists():
+        subprocess.check_call(["make", "-s", "-C", str(HERE), "ref"])
+    return REF_SO if REF_SO.exists() else None
+
+
+def c_unescape(lit: str) -> str:
+    """Decode the C string literal of oracle/_ref/model_text.inc."""
+    lit = lit.strip()
+    assert lit.startswith('"') and lit.endswith('"')
+    return lit[1:-1].replace("\\n", "\n").replace('\\"', '"').replace("\\\\", "\\")
+
+
+def reference_model_text() -> str:
+    return c_unescape(REF_MODEL_INC.read_text())
+
+
+class Oracle:
+    """The C restatement."""
+
+    def __init__(self):
+        build_oracle()
+        L = C.CDLL(str(ORACLE_SO))
+        L.gvo_model_parse.restype = C.c_void_p
+        L.gvo_model_parse.argtypes = [C.c_char_p]
+        L.gvo_model_free.argtypes = [C.c_void_p]
+        L.gvo_model_num_layers.argtypes = [C.c_void_p]
+        L.gvo_model_layer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(_f32p), C.POINTER(_f32p)]
+        L.gvo_model_set_weight_scale.argtypes = [C.c_void_p, C.c_float]
+        L.gvo_graph_forward.argtypes = [C.c_uint32, _u64p, _u32p, _u32p, _u32p, C.c_float, _f32p,
+                                        C.c_int, _f32p]
+        L.gvo_linear_forward.argtypes = [C.c_size_t, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p]
+        L.gvo_relu_forward.argtypes = [C.c_size_t, _f32p, _f32p]
+        L.gvo_sigmoid_forward.argtypes = [C.c_size_t, _f32p, _f32p]
+        L.gvo_predict.argtypes = [C.c_void_p, C.c_uint32, _u64p, _u32p, _u32p, _u32p, _f32p,
+                                  C.c_int, _f32p, C.POINTER(C.c_int)]
+        L.gvo_model_out_width.argtypes = [C.c_void_p, C.c_int]
+        self.L = L
+
+    # -- model ---------------------------------------------------------------
+    def parse(self, text: str):
+        h = self.L.gvo_model_parse(text.encode())
+        assert h, "gvo_model_parse failed"
+        return h
+
+    def free(self, h):
+        self.L.gvo_model_free(h)
+
+    def layers(self, h):
+        """[(kind, W (K x Nout) | None, bias (Nout) | None)]"""
+        out = []
+        for i in range(self.L.gvo_model_num_layers(h)):
+            r, c = C.c_int(), C.c_int()
+            W, b = _f32p(), _f32p()
+            kind = self.L.gvo_model_layer(h, i, C.byref(r), C.byref(c), C.byref(W), C.byref(b))
+            if kind == LINEAR:
+                Wm = np.ctypeslib.as_array(W, shape=(r.value, c.value)).copy()
+                bv = np.ctypeslib.as_array(b, shape=(c.value,)).copy()
+                out.append((kind, Wm, bv))
+            else:
+                out.append((kind, None, None))
+        return out
+
+    def model_from_layers(self, layers) -> str:
+        """Serialise [(kind, W, bias)] into the reference text format with
+        enough digits (%.9g) to round-trip fp32 exactly."""
+        return layers_to_text(layers)
+
+    # -- layers ----------------------------------------------------------------
+    def graph_forward(self, row_ptr, col, W, NW, scale, x):
+        n, w = x.shape
+        out = np.empty((n, 2 * w + 3), np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        self.L.gvo_graph_forward(n, _p(row_ptr, _u64p), _p(col, _u32p), _p(W, _u32p), _p(NW, _u32p),
+                                 float(scale), _p(x, _f32p), w, _p(out, _f32p))
+        return out
+
+    def linear_forward(self, x, Wm, bias):
+        n, K = x.shape
+        Nout = Wm.shape[1]
+        out = np.empty((n, Nout), np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        Wm = np.ascontiguousarray(Wm, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32)
+        self.L.gvo_linear_forward(n, K, Nout, _p(x, _f32p), _p(Wm, _f32p), _p(bias, _f32p), _p(out, _f32p))
+        return out
+
+    def relu(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty_like(x)
+        self.L.gvo_relu_forward(x.size, _p(x, _f32p), _p(out, _f32p))
+        return out
+
+    def sigmoid(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty_like(x)
+        self.L.gvo_sigmoid_forward(x.size, _p(x, _f32p), _p(out, _f32p))
+        return out
+
+    def predict(self, h, row_ptr, col, W, NW, x, scale=None):
+        if scale is not None:
+            self.L.gvo_model_set_weight_scale(h, float(scale))
+        x = np.ascontiguousarray(x, np.float32)
+        if x.ndim == 1:
+            x = x[:, None]
+        n, w = x.shape
+        ow = self.L.gvo_model_out_width(h, w)
+        out = np.empty((n, ow), np.float32)
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint64)
+        rc = self.L.gvo_predict(h, n, _p(row_ptr, _u64p), _p(col, _u32p), _p(W, _u32p), _p(NW, _u32p),
+                                _p(x, _f32p), w, _p(out, _f32p), None)
+        assert rc == 0
+        return out
+
+
+class Reference:
+    """The unmodified reference (OpenBLAS kernel pinned to Prescott)."""
+
+    def __init__(self, threads: int | None = None):
+        if not REF_SO.exists():
+            raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
+        # must be set before libopenblas' constructor runs
+        os.environ.setdefault("OPENBLAS_CORETYPE", "Prescott")
+        if threads:
+            os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
+        L = C.CDLL(str(REF_SO))
+        L.ref_blas_config.restype = C.c_char_p
+        L.ref_blas_threads.argtypes = [C.c_int]
+        L.ref_model_create.restype = C.c_void_p
+        L.ref_model_create.argtypes = [C.c_char_p]
+        L.ref_model_destroy.argtypes = [C.c_void_p]
+        L.ref_model_set_weight_scale.argtypes = [C.c_void_p, C.c_float]
+        L.ref_model_text.restype = C.c_size_t
+        L.ref_model_text.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.ref_predict.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, _u32p, _u32p, _u32p, _f32p, _f32p,
+                                  _u64p, _u32p, _u32p, C.c_int, C.POINTER(C.c_double)]
+        L.ref_graph_layer.argtypes = [C.c_uint32, C.c_uint64, _u32p, _u32p, _u32p, C.c_float, _f32p,
+                                      C.c_int, _f32p]
+        L.ref_linear_layer.argtypes = [C.c_size_t, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p]
+        L.ref_relu.argtypes = [C.c_size_t, _f32p, _f32p]
+        L.ref_sigmoid.argtypes = [C.c_size_t, _f32p, _f32p]
+        L.ref_linear_init.argtypes = [C.c_int, C.c_int, C.c_size_t, _f32p]
+        self.L = L
+        if threads:
+            L.ref_blas_threads(threads)
+
+    def blas_config(self) -> str:
+        return self.L.ref_blas_config().decode()
+
+    def model(self, text: str):
+        return self.L.ref_model_create(text.encode())
+
+    def model_text(self, h) -> str:
+        n = self.L.ref_model_text(h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.ref_model_text(h, buf, n + 1)
+        return buf.value.decode()
+
+    def destroy(self, h):
+        self.L.ref_model_destroy(h)
+
+    def predict(self, h, n, eu, ev, weights, x, scale, want_csr=False, reps=1):
+        """eu<ev sorted unique undirected edges.  Returns scores[, (row_ptr, col, NW)][, seconds]."""
+        self.L.ref_model_set_weight_scale(h, float(scale))
+        eu = np.ascontiguousarray(eu, np.uint32)
+        ev = np.ascontiguousarray(ev, np.uint32)
+        weights = np.ascontiguousarray(weights, np.uint32)
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty(n, np.float32)
+        rp = col = nw = None
+        if want_csr:
+            rp = np.empty(n + 1, np.uint64)
+            col = np.empty(2 * len(eu), np.uint32)
+            nw = np.empty(n, np.uint32)
+        sec = C.c_double()
+        rc = self.L.ref_predict(h, n, len(eu), _p(eu, _u32p), _p(ev, _u32p), _p(weights, _u32p),
+                                _p(x, _f32p), _p(out, _f32p), _p(rp, _u64p), _p(col, _u32p),
+                                _p(nw, _u32p), reps, C.byref(sec))
+        assert rc == 0 or n == 0, "reference predict returned an unexpected shape"
+        self.last_seconds = sec.value
+        if want_csr:
+            return out, (rp, col, nw)
+        return out
+
+    def graph_layer(self, n, eu, ev, weights, scale, x):
+        x = np.ascontiguousarray(x, np.float32)
+        w = x.shape[1]
+        out = np.empty((n, 2 * w + 3), np.float32)
+        eu = np.ascontiguousarray(eu, np.uint32)
+        ev = np.ascontiguousarray(ev, np.uint32)
+        weights = np.ascontiguousarray(weights, np.uint32)
+        self.L.ref_graph_layer(n, len(eu), _p(eu, _u32p), _p(ev, _u32p), _p(weights, _u32p),
+                               float(scale), _p(x, _f32p), w, _p(out, _f32p))
+        return out
+
+    def linear_layer(self, x, Wm, bias):
+        x = np.ascontiguousarray(x, np.float32)
+        Wm = np.ascontiguousarray(Wm, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32)
+        n, K = x.shape
+        out = np.empty((n, Wm.shape[1]), np.float32)
+        self.L.ref_linear_layer(n, K, Wm.shape[1], _p(x, _f32p), _p(Wm, _f32p), _p(bias, _f32p),
+                                _p(out, _f32p))
+        return out
+
+    def relu(self, x):
+        x = np.ascontiguousarray(x, np.float32).ravel()
+        out = np.empty_like(x)
+        self.L.ref_relu(x.size, _p(x, _f32p), _p(out, _f32p))
+        return out
+
+    def sigmoid(self, x):
+        x = np.ascontiguousarray(x, np.float32).ravel()
+        out = np.empty_like(x)
+        self.L.ref_sigmoid(x.size, _p(x, _f32p), _p(out, _f32p))
+        return out
+
+    def linear_init(self, K, Nout, seed):
+        out = np.empty(K * Nout + Nout, np.float32)
+        self.L.ref_linear_init(K, Nout, seed, _p(out, _f32p))
+        return out[: K * Nout].reshape(K, Nout), out[K * Nout:]
+
+
+def layers_to_text(layers, name="MWVC_Model") -> str:
+    """[(kind, W, bias)] -> reference text format (gnn_inference.cpp:92-118 layout)."""
+    parts = [name, f"{len(layers)} Layers"]
+    for kind, W, b in layers:
+        if kind == LINEAR:
+            parts.append("Linear_Layer")
+            parts.append(f"Weights: {W.shape[0]} {W.shape[1]}")
+            for row in np.asarray(W, np.float32):
+                parts.append(" ".join(f"{float(v):.9g}" for v in row) + " ")
+            parts.append("")
+            parts.append(f"Bias: 1 {len(b)}")
+            parts.append(" ".join(f"{float(v):.9g}" for v in np.asarray(b, np.float32)) + " ")
+            parts.append("")
+        elif kind == GRAPH:
+            parts.append("Graph_Layer")
+        elif kind == RELU:
+            parts.append("ReLU_Activation")
+        else:
+            parts.append("Sigmoid_Activation")
+        parts.append("")
+    return "\n".join(parts) + "\n"

@@ -1,0 +1,161 @@
+// ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// C entry points around the UNMODIFIED reference forward pass.  oracle/Makefile
+// compiles this file together with /root/reference/src/matrix.cpp and
+// /root/reference/src/gnn_inference.cpp (where they lie, never copied) against
+// /root/reference/include and the wheel-bundled OpenBLAS, into
+// oracle/_ref/libgnnref.so.  It is used to pin the C restatement
+// (oracle/gnn_oracle.c), to generate tests/golden/, and as bench.py's
+// "reference" CPU arm.  Nothing in the product links it.
+//
+// Calls into the reference:
+//   gnn::operator>>            src/gnn_inference.cpp:120-139
+//   model::set_weight_scale    src/gnn_inference.cpp:83-90
+//   model::predict             src/gnn_inference.cpp:67-81
+//   graph_layer::forward       src/gnn_inference.cpp:27-42
+//   linear_layer::forward      src/gnn_inference.cpp:20-25
+//   reduction_graph ctor       include/reduction_graph.hpp:103-128
+#include "gnn_inference.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+extern "C" {
+void openblas_set_num_threads(int n);
+char *openblas_get_config(void);
+}
+
+namespace {
+struct ref_state {
+    gnn::model m;
+    std::vector<gnn::component> parsed; // not accessible in model (private) -> layer probes use own copies
+};
+
+reduction_graph<uint32_t, uint32_t> make_graph(uint32_t n, uint64_t n_edges, const uint32_t *eu,
+                                               const uint32_t *ev, const uint32_t *w) {
+    std::vector<uint32_t> weights(w, w + n);
+    std::vector<std::pair<uint32_t, uint32_t>> edges(n_edges);
+    for (uint64_t i = 0; i < n_edges; i++) edges[i] = {eu[i], ev[i]};
+    return reduction_graph<uint32_t, uint32_t>(weights, edges);
+}
+} // namespace
+
+extern "C" {
+
+const char *ref_blas_config() { return openblas_get_config(); }
+void ref_blas_threads(int n) { openblas_set_num_threads(n); }
+
+void *ref_model_create(const char *text) {
+    auto *s = new ref_state();
+    std::string src(text);
+    std::istringstream is(src);
+    is >> s->m;
+    return s;
+}
+
+void ref_model_destroy(void *h) { delete static_cast<ref_state *>(h); }
+
+void ref_model_set_weight_scale(void *h, float ws) { static_cast<ref_state *>(h)->m.set_weight_scale(ws); }
+
+// Serialise through the reference's operator<< (gnn_inference.cpp:92-118).
+// Returns the number of bytes needed (excluding NUL); copies up to cap-1.
+size_t ref_model_text(void *h, char *buf, size_t cap) {
+    std::ostringstream os;
+    os << static_cast<ref_state *>(h)->m;
+    std::string t = os.str();
+    if (cap) {
+        size_t k = t.size() < cap - 1 ? t.size() : cap - 1;
+        std::memcpy(buf, t.data(), k);
+        buf[k] = 0;
+    }
+    return t.size();
+}
+
+// The graph is given as the sorted, de-duplicated list of undirected edges
+// (u < v) that parse_graph (src/GNN_VC.cpp:34-91) would hand to the
+// reduction_graph ctor.  x: n floats, out: n floats.  If csr_* are non-null the
+// CSR as seen through g.begin(u)/end(u) (and g.NW) is written back so callers
+// can feed the very same adjacency order to the code under test.
+int ref_predict(void *h, uint32_t n, uint64_t n_edges, const uint32_t *eu, const uint32_t *ev,
+                const uint32_t *w, const float *x, float *out, uint64_t *csr_row_ptr,
+                uint32_t *csr_col, uint32_t *nw_out, int reps, double *best_seconds) {
+    auto *s = static_cast<ref_state *>(h);
+    auto g = make_graph(n, n_edges, eu, ev, w);
+    if (csr_row_ptr) {
+        uint64_t p = 0;
+        for (uint32_t u = 0; u < n; u++) {
+            csr_row_ptr[u] = p;
+            for (auto it = g.begin(u); it != g.end(u); ++it) csr_col[p++] = *it;
+        }
+        csr_row_ptr[n] = p;
+    }
+    if (nw_out)
+        for (uint32_t u = 0; u < n; u++) nw_out[u] = g.NW(u);
+    matrix in(n, 1), res;
+    for (uint32_t u = 0; u < n; u++) in(u, 0) = x[u];
+    double best = 1e300;
+    if (reps < 1) reps = 1;
+    for (int r = 0; r < reps; r++) {
+        auto t0 = std::chrono::steady_clock::now();
+        s->m.predict(in, res, g);
+        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (dt < best) best = dt;
+    }
+    if (best_seconds) *best_seconds = best;
+    if (res.get_height() != n || (n && res.get_width() != 1)) return -1;
+    for (uint32_t u = 0; u < n; u++) out[u] = res(u, 0);
+    return 0;
+}
+
+// graph_layer::forward alone: in n x w  ->  out n x (2w+3)
+int ref_graph_layer(uint32_t n, uint64_t n_edges, const uint32_t *eu, const uint32_t *ev,
+                    const uint32_t *w, float scale, const float *in, int width, float *out) {
+    auto g = make_graph(n, n_edges, eu, ev, w);
+    gnn::graph_layer gl;
+    gl.WEIGHT_SCALE = scale;
+    matrix a(n, width), b;
+    std::copy(in, in + (size_t)n * width, a.raw().begin());
+    gl.forward(a, b, g);
+    std::copy(b.raw().begin(), b.raw().end(), out);
+    return (int)b.get_width();
+}
+
+// linear_layer::forward alone: in n x K, W K x Nout, bias Nout -> out n x Nout
+void ref_linear_layer(size_t n, int K, int Nout, const float *in, const float *W,
+                      const float *bias, float *out) {
+    gnn::linear_layer l(K, Nout, 0);
+    std::copy(W, W + (size_t)K * Nout, l.W.raw().begin());
+    std::copy(bias, bias + Nout, l.bias.raw().begin());
+    matrix a(n, K), b;
+    std::copy(in, in + n * (size_t)K, a.raw().begin());
+    l.forward(a, b);
+    std::copy(b.raw().begin(), b.raw().end(), out);
+}
+
+void ref_relu(size_t n, const float *in, float *out) {
+    matrix a(n, 1), b;
+    std::copy(in, in + n, a.raw().begin());
+    gnn::ReLU().forward(a, b);
+    std::copy(b.raw().begin(), b.raw().end(), out);
+}
+
+void ref_sigmoid(size_t n, const float *in, float *out) {
+    matrix a(n, 1), b;
+    std::copy(in, in + n, a.raw().begin());
+    gnn::sigmoid().forward(a, b);
+    std::copy(b.raw().begin(), b.raw().end(), out);
+}
+
+// linear_layer random init (gnn_inference.cpp:7-18), for API-parity tests of
+// the drop-in host code: returns K*Nout weights followed by Nout bias values.
+void ref_linear_init(int K, int Nout, size_t seed, float *out) {
+    gnn::linear_layer l(K, Nout, seed);
+    std::copy(l.W.raw().begin(), l.W.raw().end(), out);
+    std::copy(l.bias.raw().begin(), l.bias.raw().end(), out + (size_t)K * Nout);
+}
+
+} // extern "C"

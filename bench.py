@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- GNN forward (gnn::model::predict) throughput in undirected edges/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode exact|fast] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): R-MAT, Graph500
+parameters (0.57, 0.19, 0.19, 0.05), scale 20, edge factor 16, symmetrised and
+de-duplicated, integer weights 1..200, trained GNN_VC weights (tests/golden).  For
+N > 1 GPUs the scale grows by log2(N) (weak scaling: fixed work per GPU; N = 8 is
+scale 23, 8.4 M vertices / ~128 M edges, BASELINE configs[3]); the graph is cut
+into work-balanced vertex ranges and the 16-float rows are exchanged between
+stages over NCCL.  A "step" is one whole forward: x -> scores.
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput, `e2e`
+goes through the host-buffer C ABI call (pinned H2D of x, D2H of the scores).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "gnn_forward_edges_per_sec"
+UNIT = "edges/s"
+
+
+def rmat_scale_for(n_gpus: int) -> int:
+    return 20 + max(0, int(round(np.log2(n_gpus))))
+
+
+def algorithmic_bytes(n: int, m: int):
+    """fp32 rows, uint32 ids/offsets, no-reuse gather model, per stage."""
+    s0 = 8 * m + 80 * n
+    s1 = 68 * m + 140 * n
+    s2 = 68 * m + 80 * n
+    return s0, s1, s2
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons during the timed region, via NVML (5 ms period)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10,
+                 "applications_clocks": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref), or the oracle port
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    import gnn_mwvc_b200  # noqa: F401
+    from gnn_mwvc_b200 import capi, graphs
+    from oracle import pyoracle as po
+
+    cores = os.cpu_count() or 1
+    layers = capi.load_model_npz(ROOT / "tests" / "golden" / "mwvc_model.npz")
+    text = po.layers_to_text(layers)
+    # bounded sample of the same workload: same generator and parameters, smaller scale
+    sample_scale = 17 if (args.steps + args.warmup) <= 40 else 15
+    g = graphs.rmat_graph(sample_scale, 16, seed=42, device="cpu")
+    rp, col, W, NW = g.numpy()
+    eu, ev = g.edges_numpy()
+    scale = 200.0
+    x = W.astype(np.float32) / np.float32(scale)
+    if po.REF_SO.exists():
+        ref = po.Reference(threads=cores)
+        h = ref.model(text)
+        kind = "reference"
+
+        def step():
+            ref.predict(h, g.n, eu, ev, W, x, scale)
+            return ref.last_seconds            # predict only; graph construction excluded
+    else:
+        orc = po.Oracle()
+        h = orc.parse(text)
+        kind, cores = "port", 1
+
+        def step():
+            t = time.perf_counter()
+            orc.predict(h, rp, col, W, NW, x, scale)
+            return time.perf_counter() - t
+    for _ in range(args.warmup):
+        step()
+    secs = [step() for _ in range(args.steps)]
+    total = float(np.sum(secs))
+    value = g.n_edges * args.steps / total
+    sample = f"R-MAT scale {sample_scale} ef 16 (n={g.n}, E={g.n_edges}), predict() only, {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"rmat_scale{rmat_scale_for(args.gpus)}_ef16 (timed on the bounded sample below)",
+                   "sample": sample, "mode": "reference CPU (OpenBLAS)" if kind == "reference" else "oracle port"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_leg(layers, budget_s: float = 20.0):
+    """Rank 0, N=1: the reference CPU path on a bounded sample (~10-30 s of CPU work)."""
+    import gnn_mwvc_b200  # noqa: F401
+    from gnn_mwvc_b200 import graphs
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    text = po.layers_to_text(layers)
+    g = graphs.rmat_graph(17, 16, seed=42, device="cpu")
+    rp, col, W, NW = g.numpy()
+    scale = 200.0
+    x = W.astype(np.float32) / np.float32(scale)
+    t_all = time.perf_counter()
+    secs = []
+    if po.REF_SO.exists():
+        ref = po.Reference(threads=cores)
+        h = ref.model(text)
+        eu, ev = g.edges_numpy()
+        kind = "reference"
+        while len(secs) < 3 or (time.perf_counter() - t_all < budget_s and len(secs) < 12):
+            ref.predict(h, g.n, eu, ev, W, x, scale)
+            secs.append(ref.last_seconds)
+    else:
+        orc = po.Oracle()
+        h = orc.parse(text)
+        kind, cores = "port", 1
+        while len(secs) < 2 or (time.perf_counter() - t_all < budget_s and len(secs) < 8):
+            t = time.perf_counter()
+            orc.predict(h, rp, col, W, NW, x, scale)
+            secs.append(time.perf_counter() - t)
+    best = float(np.median(secs[1:])) if len(secs) > 1 else secs[0]
+    return {"value": g.n_edges / best, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"R-MAT scale 17 ef 16 (n={g.n}, E={g.n_edges}), median of {len(secs) - 1} warm predict() calls, "
+                      f"{best * 1e3:.0f} ms each"}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gnn_mwvc_b200 as pkg
+    from gnn_mwvc_b200 import capi, graphs
+    from gnn_mwvc_b200 import dist as gdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libgvc has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    mode = pkg.MODE_EXACT if args.mode == "exact" else pkg.MODE_FAST
+    layers = capi.load_model_npz(ROOT / "tests" / "golden" / "mwvc_model.npz")
+    scale_log2 = args.scale if args.scale else rmat_scale_for(world)
+
+    # ---- synthetic graph, generated on the GPU (every rank builds the same graph) ----------
+    t0 = time.perf_counter()
+    if args.workload == "rmat":
+        g = graphs.rmat_graph(scale_log2, 16, seed=42, device=dev)
+        wl_name = f"rmat_scale{scale_log2}_ef16"
+    elif args.workload == "grid":
+        side = int(round((20_000_000 * world) ** 0.5))
+        g = graphs.grid_graph(side, side, device=dev)
+        wl_name = f"grid_{side}x{side}"
+    else:
+        g = graphs.er_graph(10000 * world, 50000 * world, seed=1, device=dev)
+        wl_name = f"er_{g.n}_{g.n_edges}"
+    n, m, e_total = g.n, g.nnz, g.n_edges
+    weight_scale = 200.0
+    x_full = (g.weights.to(torch.float32) / weight_scale).contiguous()
+    bounds = graphs.nnz_balanced_ranges(g.row_ptr, world) if world > 1 else [0, n]
+    shard = gdist.make_shard(g, bounds, rank)
+    rp32 = shard.row_ptr.to(torch.int32).contiguous()
+    g.eu = g.ev = None
+    gen_s = time.perf_counter() - t0
+
+    ctx = pkg.Context(local_rank)
+    ctx.model_upload(layers)
+    ctx.graph_adopt(rp32, shard.col, shard.weights, shard.nw, n_global=n, v_begin=shard.v_begin, v_end=shard.v_end)
+    stream = ctx.torch_stream()
+    h1 = torch.zeros(n, 16, device=dev)
+    h2 = torch.zeros(n, 16, device=dev)
+    scores = torch.zeros(shard.n_local, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def forward_once():
+        if world == 1:
+            ctx.forward_device(x_full, weight_scale, scores, mode)
+        else:
+            gdist.sharded_forward(ctx.stage_device, shard, x_full, h1, h2, scores, weight_scale, mode)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            forward_once()
+        barrier()
+        # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        launches0 = ctx.launches
+        with ClockSampler(local_rank) as clk:
+            barrier()
+            for i in range(args.steps):
+                flush.fill_(i & 0xFF)
+                starts[i].record(stream)
+                forward_once()
+                ends[i].record(stream)
+            barrier()
+        launches = ctx.launches - launches0
+        step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        total_ms = float(np.sum(step_ms))
+
+        # ---- per-stage kernel timing for the roofline (dominant kernel = stage 1) ----------------
+        stage_ms = [[], [], []]
+        if world == 1:
+            for rep in range(max(5, min(args.steps, 20))):
+                for st, (src, dst) in enumerate(((x_full, h1), (h1, h2), (h2, scores))):
+                    flush.fill_(rep & 0xFF)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    ctx.stage_device(st, src, dst, weight_scale, mode)
+                    b.record(stream)
+                    b.synchronize()
+                    stage_ms[st].append(a.elapsed_time(b))
+        torch.cuda.synchronize()
+
+    # max over ranks of the per-rank timed total
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = e_total * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer API ------------------------------------------------
+    e2e = None
+    x_host = x_full.cpu().numpy()
+    if world == 1:
+        for _ in range(3):
+            ctx.forward(x_host, weight_scale, mode)
+        k = max(3, min(args.steps, 50))
+        t1 = time.perf_counter()
+        for _ in range(k):
+            out_host = ctx.forward(x_host, weight_scale, mode)
+        e2e_s = (time.perf_counter() - t1) / k
+        e2e = {"value": e_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * n),
+               "d2h_bytes_per_step": int(4 * n), "ms_per_step": e2e_s * 1e3,
+               "what": "gvc_forward(): pinned H2D of x, 3 fused kernels, D2H of the scores; CSR resident (uploaded once)"}
+        assert np.isfinite(out_host).all()
+    else:
+        xp = torch.from_numpy(x_host).pin_memory()
+        sp = torch.empty(shard.n_local, dtype=torch.float32).pin_memory()
+        xd = torch.empty_like(x_full)
+        k = max(3, min(args.steps, 50))
+        with torch.cuda.stream(stream):
+            def e2e_step():
+                xd.copy_(xp, non_blocking=True)
+                gdist.sharded_forward(ctx.stage_device, shard, xd, h1, h2, scores, weight_scale, mode)
+                sp.copy_(scores, non_blocking=True)
+                stream.synchronize()
+            for _ in range(3):
+                e2e_step()
+            barrier()
+            t1 = time.perf_counter()
+            for _ in range(k):
+                e2e_step()
+            barrier()
+            e2e_s = (time.perf_counter() - t1) / k
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        e2e = {"value": e_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * n) * world,
+               "d2h_bytes_per_step": int(4 * n), "ms_per_step": e2e_s * 1e3,
+               "what": "per rank: pinned H2D of x (replicated), 3 fused kernels + 2 NCCL row exchanges, D2H of its score slice"}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        b0, b1, b2 = algorithmic_bytes(n, m)
+        roof = None
+        if world == 1 and stage_ms[1]:
+            t_s1 = float(np.mean(stage_ms[1])) * 1e-3
+            ach = b1 / t_s1 / 1e9
+            traffic = None
+            tp = ROOT / "profiles" / "traffic.json"
+            if tp.exists():
+                traffic = json.loads(tp.read_text()).get(f"stage1_{args.mode}")
+            roof = {"bound": "hbm", "kernel": f"stage_kernel<1,{args.mode}> (graph layer w=16 + 35->32->32->16)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": b1,
+                    "avg_launch_ms": t_s1 * 1e3,
+                    "stage_ms": [float(np.mean(s)) for s in stage_ms],
+                    "forward_frac": (b0 + b1 + b2) / (total_ms / args.steps * 1e-3) / 1e9 / peak}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_leg(layers)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "vertices": n, "edges": e_total, "nnz": m, "mode": args.mode,
+                       "weights": "trained GNN_VC model (tests/golden/mwvc_model.npz)",
+                       "l2": "256 MiB flush write between timed steps; working set (CSR + rows) also exceeds the 126 MB L2",
+                       "sharding": "single GPU" if world == 1 else f"{world} work-balanced vertex ranges, NCCL all-gather of 16-float rows after stages 0 and 1",
+                       "graph_generation_s": round(gen_s, 2)},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu,
+            "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--workload", default="rmat", choices=["rmat", "grid", "er"])
+    ap.add_argument("--scale", type=int, default=0, help="override the R-MAT scale")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,294 @@
+"""ctypes binding of libgvc.so (include/gvc.h) -- the product's only compute path.
+
+There is deliberately no fallback: if the shared library is missing, or no B200
+is visible, importing works but every compute call raises.  Nothing here touches
+``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libgvc.so"
+
+LINEAR, GRAPH, RELU, SIGMOID = 0, 1, 2, 3
+MODE_EXACT, MODE_FAST = 0, 1
+
+_f32p = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_i32p = C.POINTER(C.c_int)
+
+# every symbol include/gvc.h declares: (restype, argtypes)
+SIGNATURES = {
+    "gvc_last_error": (C.c_char_p, []),
+    "gvc_abi_version": (C.c_int, []),
+    "gvc_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "gvc_ctx_destroy": (None, [C.c_void_p]),
+    "gvc_model_upload": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p, _i32p, C.POINTER(_f32p), C.POINTER(_f32p)]),
+    "gvc_model_is_fused": (C.c_int, [C.c_void_p]),
+    "gvc_graph_upload": (C.c_int, [C.c_void_p, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
+    "gvc_graph_upload_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
+    "gvc_graph_adopt_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gvc_forward": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, C.c_int]),
+    "gvc_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]),
+    "gvc_stage_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int]),
+    "gvc_graph_layer_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float]),
+    "gvc_linear_layer_device": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "gvc_relu_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "gvc_sigmoid_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),
+    "gvc_graph_layer_host": (C.c_int, [C.c_void_p, _f32p, C.c_int, _f32p, C.c_float]),
+    "gvc_linear_host": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_int]),
+    "gvc_relu_host": (C.c_int, [C.c_void_p, C.c_uint64, _f32p, _f32p]),
+    "gvc_sigmoid_host": (C.c_int, [C.c_void_p, C.c_uint64, _f32p, _f32p, C.c_int]),
+    "gvc_sgemm_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, _f32p, C.c_uint64,
+                                 _f32p, C.c_uint64, C.c_float, _f32p, C.c_uint64]),
+    "gvc_stream": (C.c_void_p, [C.c_void_p]),
+    "gvc_sync": (C.c_int, [C.c_void_p]),
+    "gvc_launch_count": (C.c_uint64, [C.c_void_p]),
+    "gvc_debug_h": (C.c_void_p, [C.c_void_p, C.c_int]),
+}
+
+
+class GvcError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: Path | None = None):
+    """dlopen libgvc.so and type every symbol of include/gvc.h.  Raises if missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise GvcError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(ty) if a is not None and a.size else None
+
+
+def _dptr(t):
+    """Device pointer of a torch tensor (or a raw int)."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One gvc_ctx: a device, its stream, one model and one graph shard."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        self._check(self.lib.gvc_ctx_create(C.byref(h), device))
+        self.h = h
+        self.device = device
+        self.n_global = 0
+        self.v_begin = 0
+        self.v_end = 0
+        self._keep = []      # adopted torch tensors must outlive the context's use of them
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GvcError(f"libgvc error {rc}: {self.lib.gvc_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gvc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- model ---------------------------------------------------------------
+    def model_upload(self, layers):
+        """layers: [(kind, W (K x Nout) | None, bias (Nout) | None)]"""
+        n = len(layers)
+        kinds = (C.c_int * n)(*[int(k) for k, _, _ in layers])
+        rows = (C.c_int * n)()
+        cols = (C.c_int * n)()
+        Wp = (_f32p * n)()
+        bp = (_f32p * n)()
+        keep = []
+        for i, (k, W, b) in enumerate(layers):
+            if k == LINEAR:
+                W = _np(W, np.float32)
+                b = _np(b, np.float32).ravel()
+                rows[i], cols[i] = W.shape
+                Wp[i] = W.ctypes.data_as(_f32p)
+                bp[i] = b.ctypes.data_as(_f32p)
+                keep += [W, b]
+        self._check(self.lib.gvc_model_upload(self.h, n, kinds, rows, cols, Wp, bp))
+        self.layers = layers
+
+    @property
+    def fused(self) -> bool:
+        return bool(self.lib.gvc_model_is_fused(self.h))
+
+    # -- graph ---------------------------------------------------------------
+    def graph_upload(self, row_ptr, col, W, NW, n_global=None, v_begin=0, v_end=None):
+        row_ptr = _np(row_ptr, np.uint64)
+        col = _np(col, np.uint32)
+        W = _np(W, np.uint32)
+        NW = _np(NW, np.uint32)
+        nl = len(row_ptr) - 1
+        if n_global is None:
+            n_global = nl
+        if v_end is None:
+            v_end = v_begin + nl
+        self._check(self.lib.gvc_graph_upload_shard(self.h, n_global, v_begin, v_end, _ptr(row_ptr, _u64p),
+                                                    _ptr(col, _u32p), _ptr(W, _u32p), _ptr(NW, _u32p)))
+        self.n_global, self.v_begin, self.v_end = n_global, v_begin, v_end
+
+    def graph_adopt(self, row_ptr_i32, col_i32, W_i32, NW_i32, n_global=None, v_begin=0, v_end=None):
+        """Device-resident shard: torch int32 CUDA tensors (bit patterns of uint32)."""
+        nl = row_ptr_i32.numel() - 1
+        if n_global is None:
+            n_global = nl
+        if v_end is None:
+            v_end = v_begin + nl
+        self._keep = [row_ptr_i32, col_i32, W_i32, NW_i32]
+        self._check(self.lib.gvc_graph_adopt_device(self.h, n_global, v_begin, v_end, _dptr(row_ptr_i32),
+                                                    _dptr(col_i32), _dptr(W_i32), _dptr(NW_i32)))
+        self.n_global, self.v_begin, self.v_end = n_global, v_begin, v_end
+
+    # -- forward ---------------------------------------------------------------
+    def forward(self, x, weight_scale: float, mode: int = MODE_EXACT) -> np.ndarray:
+        """Host in, host out: gnn::model::predict."""
+        x = _np(x, np.float32).ravel()
+        if x.size != self.n_global:
+            raise GvcError(f"x has {x.size} entries, graph has {self.n_global} vertices")
+        out = np.empty(self.n_global, np.float32)
+        self._check(self.lib.gvc_forward(self.h, _ptr(x, _f32p), float(weight_scale), _ptr(out, _f32p), mode))
+        return out
+
+    def forward_device(self, d_x, weight_scale: float, d_scores, mode: int = MODE_EXACT):
+        self._check(self.lib.gvc_forward_device(self.h, _dptr(d_x), float(weight_scale), _dptr(d_scores), mode))
+
+    def stage_device(self, stage: int, d_in, d_out, weight_scale: float, mode: int = MODE_EXACT):
+        self._check(self.lib.gvc_stage_device(self.h, stage, _dptr(d_in), _dptr(d_out), float(weight_scale), mode))
+
+    def graph_layer_device(self, d_in, width: int, d_out, weight_scale: float):
+        self._check(self.lib.gvc_graph_layer_device(self.h, _dptr(d_in), width, _dptr(d_out), float(weight_scale)))
+
+    def linear_layer_device(self, layer_index: int, n: int, d_in, d_out):
+        self._check(self.lib.gvc_linear_layer_device(self.h, layer_index, n, _dptr(d_in), _dptr(d_out)))
+
+    def relu_device(self, count: int, d_in, d_out):
+        self._check(self.lib.gvc_relu_device(self.h, count, _dptr(d_in), _dptr(d_out)))
+
+    def sigmoid_device(self, count: int, d_in, d_out, mode: int = MODE_EXACT):
+        self._check(self.lib.gvc_sigmoid_device(self.h, count, _dptr(d_in), _dptr(d_out), mode))
+
+    # -- host-buffer single layers (what the drop-in layer structs call) -----------
+    def graph_layer_host(self, x, weight_scale: float) -> np.ndarray:
+        x = _np(x, np.float32)
+        n, w = x.shape
+        out = np.empty((n, 2 * w + 3), np.float32)
+        self._check(self.lib.gvc_graph_layer_host(self.h, _ptr(x, _f32p), w, _ptr(out, _f32p), float(weight_scale)))
+        return out
+
+    def linear_host(self, x, W, bias, mode: int = MODE_EXACT) -> np.ndarray:
+        x, W, bias = _np(x, np.float32), _np(W, np.float32), _np(bias, np.float32).ravel()
+        n, K = x.shape
+        out = np.empty((n, W.shape[1]), np.float32)
+        self._check(self.lib.gvc_linear_host(self.h, n, K, W.shape[1], _ptr(x, _f32p), _ptr(W, _f32p),
+                                             _ptr(bias, _f32p), _ptr(out, _f32p), mode))
+        return out
+
+    def relu_host(self, x) -> np.ndarray:
+        x = _np(x, np.float32)
+        out = np.empty_like(x)
+        self._check(self.lib.gvc_relu_host(self.h, x.size, _ptr(x, _f32p), _ptr(out, _f32p)))
+        return out
+
+    def sigmoid_host(self, x, mode: int = MODE_EXACT) -> np.ndarray:
+        x = _np(x, np.float32)
+        out = np.empty_like(x)
+        self._check(self.lib.gvc_sigmoid_host(self.h, x.size, _ptr(x, _f32p), _ptr(out, _f32p), mode))
+        return out
+
+    def sgemm_host(self, A, B, C0=None, trans_a=False, trans_b=False, beta: float = 0.0) -> np.ndarray:
+        A, B = _np(A, np.float32), _np(B, np.float32)
+        m = A.shape[1] if trans_a else A.shape[0]
+        k = A.shape[0] if trans_a else A.shape[1]
+        n = B.shape[0] if trans_b else B.shape[1]
+        out = np.zeros((m, n), np.float32) if C0 is None else _np(C0, np.float32).copy()
+        self._check(self.lib.gvc_sgemm_host(self.h, int(trans_a), int(trans_b), m, n, k, _ptr(A, _f32p), A.shape[1],
+                                            _ptr(B, _f32p), B.shape[1], float(beta), _ptr(out, _f32p), n))
+        return out
+
+    # -- plumbing ----------------------------------------------------------------
+    @property
+    def stream_ptr(self) -> int:
+        return int(self.lib.gvc_stream(self.h) or 0)
+
+    def torch_stream(self):
+        import torch
+        return torch.cuda.ExternalStream(self.stream_ptr, device=torch.device("cuda", self.device))
+
+    def sync(self):
+        self._check(self.lib.gvc_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.gvc_launch_count(self.h))
+
+
+def load_model_npz(path):
+    """tests/golden/mwvc_model.npz -> [(kind, W, bias)]"""
+    z = np.load(path)
+    kinds = z["kinds"]
+    layers = []
+    for i, k in enumerate(kinds):
+        if int(k) == LINEAR:
+            layers.append((LINEAR, z[f"W{i}"], z[f"b{i}"]))
+        else:
+            layers.append((int(k), None, None))
+    return layers
+
+
+def random_model(seed: int = 0):
+    """The GNN_VC architecture with random weights,
+    uniform(+-1/sqrt(K+1)) like linear_layer's ctor (reference src/gnn_inference.cpp:7-18)."""
+    rng = np.random.default_rng(seed)
+    dims = [(5, 32), (32, 32), (32, 16), (35, 32), (32, 32), (32, 16), (35, 32), (32, 16), (16, 1)]
+    it = iter(dims)
+    layers = []
+    pattern = [GRAPH, LINEAR, RELU, LINEAR, RELU, LINEAR, RELU,
+               GRAPH, LINEAR, RELU, LINEAR, RELU, LINEAR, RELU,
+               GRAPH, LINEAR, RELU, LINEAR, RELU, LINEAR, SIGMOID]
+    for k in pattern:
+        if k == LINEAR:
+            K, N = next(it)
+            lim = 1.0 / np.sqrt(K + 1)
+            layers.append((LINEAR, rng.uniform(-lim, lim, (K, N)).astype(np.float32),
+                           rng.uniform(-lim, lim, N).astype(np.float32)))
+        else:
+            layers.append((k, None, None))
+    return layers

@@ -1,0 +1,732 @@
+// gvc_api.cu -- the C ABI of include/gvc.h on top of the sm_100a kernels.
+//
+// Host-side counterpart of gnn::model::predict (reference
+// src/gnn_inference.cpp:67-81): owns the device copies of the model and of the
+// graph's CSR view, picks the fused three-stage path for the GNN_VC
+// architecture or the per-layer path for any other layer
+// sequence, and enqueues everything on one stream.  No CPU fallback exists: if
+// CUDA is unusable every entry point reports an error.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gvc.h"
+#include "gvc_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define GVC_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(1000 + (int)e_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+struct HostLayer {
+    int kind = 0, rows = 0, cols = 0;
+    std::vector<float> W, b;
+    float *dW = nullptr, *db = nullptr;
+};
+
+template <typename T>
+struct DevBuf {   // grow-only device buffer
+    T *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) return fail(GVC_ERR_ALLOC, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {   // grow-only pinned host buffer
+    T *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        if (e != cudaSuccess) return fail(GVC_ERR_ALLOC, "cudaMallocHost(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct gvc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+
+    // model
+    std::vector<HostLayer> layers;
+    bool fused = false;
+    float *d_stage_params[3] = {nullptr, nullptr, nullptr};
+
+    // graph shard
+    bool have_graph = false;
+    uint32_t n_global = 0, v_begin = 0, v_end = 0;
+    uint64_t nnz = 0;
+    const uint32_t *row_ptr = nullptr, *col = nullptr, *Wv = nullptr, *NWv = nullptr;   // device views
+    DevBuf<uint32_t> own_row_ptr, own_col, own_W, own_NW;
+    PinBuf<uint32_t> stage_u32;
+
+    // activations
+    DevBuf<float> d_x, d_h1, d_h2, d_scores, d_ping, d_pong;
+    PinBuf<float> pin_x, pin_scores;
+
+    uint32_t n_local() const { return v_end - v_begin; }
+};
+
+namespace {
+
+using namespace gvc;
+
+const int kFusedKinds[21] = {GVC_GRAPH, GVC_LINEAR, GVC_RELU, GVC_LINEAR, GVC_RELU, GVC_LINEAR, GVC_RELU,
+                             GVC_GRAPH, GVC_LINEAR, GVC_RELU, GVC_LINEAR, GVC_RELU, GVC_LINEAR, GVC_RELU,
+                             GVC_GRAPH, GVC_LINEAR, GVC_RELU, GVC_LINEAR, GVC_RELU, GVC_LINEAR, GVC_SIGMOID};
+const int kFusedDims[9][2] = {{5, 32}, {32, 32}, {32, 16}, {35, 32}, {32, 32}, {32, 16}, {35, 32}, {32, 16}, {16, 1}};
+
+bool detect_fused(const std::vector<HostLayer> &L) {
+    if (L.size() != 21) return false;
+    int li = 0;
+    for (int i = 0; i < 21; ++i) {
+        if (L[i].kind != kFusedKinds[i]) return false;
+        if (L[i].kind == GVC_LINEAR) {
+            if (L[i].rows != kFusedDims[li][0] || L[i].cols != kFusedDims[li][1]) return false;
+            for (float v : L[i].W) if (!std::isfinite(v)) return false;   // dropping rows 32..34 needs finite weights
+            for (float v : L[i].b) if (!std::isfinite(v)) return false;
+            ++li;
+        }
+    }
+    return true;
+}
+
+// Pack one stage's three dense layers as gvc_kernels.cuh's StageDims describes.
+std::vector<float> pack_stage(const std::vector<HostLayer> &L, int stage) {
+    std::vector<const HostLayer *> lin;
+    for (auto &l : L) if (l.kind == GVC_LINEAR) lin.push_back(&l);
+    const StageDims D = stage_dims(stage);
+    const int K[3] = {D.Ka, D.Kb, D.Kc}, N[3] = {D.Na, D.Nb, D.Nc};
+    std::vector<float> out;
+    for (int j = 0; j < 3; ++j) {
+        const HostLayer *l = lin[stage * 3 + j];
+        out.insert(out.end(), l->W.begin(), l->W.begin() + (size_t)K[j] * N[j]);   // first K rows (drops 32..34 of 35)
+        out.insert(out.end(), l->b.begin(), l->b.begin() + N[j]);
+    }
+    return out;
+}
+
+// ---- generic per-layer kernels (any layer sequence) ------------------------------
+
+// graph_layer::forward :27-42, one thread per output element
+__global__ void generic_graph_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                                     const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+                                     const float *__restrict__ in, int w, float *__restrict__ out,
+                                     uint32_t n_local, uint32_t v_begin, float scale) {
+    const int ow = 2 * w + 3;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_local * ow) return;
+    const uint32_t u = (uint32_t)(idx / ow);
+    const int c = (int)(idx % ow);
+    const uint32_t beg = row_ptr[u], end = row_ptr[u + 1];
+    float v = 0.0f;
+    if (c < w) {
+        for (uint32_t e = beg; e < end; ++e) v = __fadd_rn(v, in[(size_t)col[e] * w + c]);
+    } else if (c < 2 * w) {
+        v = in[(size_t)(v_begin + u) * w + (c - w)];
+    }
+    if (c == w + 1) v = __uint2float_rn(end - beg);
+    if (c == w + 2) v = __fdiv_rn(__uint2float_rn(Wv[u]), scale);
+    if (c == w + 3) v = __fdiv_rn(__uint2float_rn(NWv[u]), scale);
+    out[idx] = v;
+}
+
+// linear_layer::forward :20-25 in the operation order of oracle/gnn_oracle.c
+template <bool EXACT>
+__global__ void generic_linear_kernel(const float *__restrict__ in, int K, int Nout,
+                                      const float *__restrict__ Wm, const float *__restrict__ bias,
+                                      float *__restrict__ out, uint64_t n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * (uint64_t)Nout) return;
+    const uint64_t i = idx / Nout;
+    const int j = (int)(idx % Nout);
+    const float *a = in + i * K;
+    float r;
+    if (!EXACT) {
+        float acc = 0.0f;
+        for (int k = 0; k < K; ++k) acc = fmaf(a[k], Wm[(size_t)k * Nout + j], acc);
+        r = acc;
+    } else {
+        const bool last_odd = (n & 1) && i == n - 1;
+        const int K8 = K / 8 * 8;
+        if (Nout == 1 && last_odd) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            int k = 0;
+            for (; k < K8; ++k) c[k & 3] = __fadd_rn(c[k & 3], __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
+            for (; k < K; ++k) c[0] = __fadd_rn(c[0], __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
+            r = __fadd_rn(__fadd_rn(c[0], c[1]), __fadd_rn(c[2], c[3]));
+        } else if (Nout == 1 || last_odd) {
+            float ev = 0.0f, od = 0.0f;
+            int k = 0;
+            for (; k < K8; k += 2) {
+                ev = __fadd_rn(ev, __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
+                od = __fadd_rn(od, __fmul_rn(a[k + 1], Wm[(size_t)(k + 1) * Nout + j]));
+            }
+            for (; k < K; ++k) ev = __fadd_rn(ev, __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
+            r = __fadd_rn(ev, od);
+        } else {
+            float acc = 0.0f;
+            for (int k = 0; k < K; ++k) acc = __fadd_rn(acc, __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
+            r = acc;
+        }
+    }
+    out[idx] = __fadd_rn(r, bias[j]);
+}
+
+__global__ void generic_relu_kernel(const float *__restrict__ in, float *__restrict__ out, uint64_t count) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < count) out[idx] = relu_ref(in[idx]);
+}
+
+template <bool EXACT>
+__global__ void generic_sigmoid_kernel(const float *__restrict__ in, float *__restrict__ out, uint64_t count) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < count) out[idx] = sigmoid_ref<EXACT>(in[idx]);
+}
+
+// dot(), src/matrix.cpp:106-122: C = op(A) op(B) + beta C, one thread per element of C
+__global__ void generic_sgemm_kernel(int ta, int tb, uint64_t m, uint64_t n, uint64_t k,
+                                     const float *__restrict__ A, uint64_t lda, const float *__restrict__ B,
+                                     uint64_t ldb, float beta, float *__restrict__ Cm, uint64_t ldc) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * n) return;
+    const uint64_t i = idx / n, j = idx % n;
+    float acc = 0.0f;
+    for (uint64_t p = 0; p < k; ++p) {
+        const float a = ta ? A[p * lda + i] : A[i * lda + p];
+        const float b = tb ? B[j * ldb + p] : B[p * ldb + j];
+        acc = __fadd_rn(acc, __fmul_rn(a, b));
+    }
+    float *c = Cm + i * ldc + j;
+    *c = beta == 0.0f ? acc : __fadd_rn(acc, __fmul_rn(beta, *c));
+}
+
+inline unsigned blocks_for(uint64_t work, int threads) { return (unsigned)((work + threads - 1) / threads); }
+
+template <int STAGE>
+int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int mode) {
+    const uint32_t nl = c->n_local();
+    if (nl == 0) return 0;
+    const unsigned grid = (nl + kWarpsPerCta * kTileVerts - 1) / (kWarpsPerCta * kTileVerts);
+    const size_t smem = stage_smem_bytes<STAGE>();
+    if (mode == GVC_MODE_EXACT) {
+        stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
+            c->row_ptr, c->col, c->Wv, c->NWv, d_in, d_out, c->d_stage_params[STAGE], nl, c->v_begin, scale);
+    } else {
+        stage_kernel<STAGE, false><<<grid, kCtaThreads, smem, c->stream>>>(
+            c->row_ptr, c->col, c->Wv, c->NWv, d_in, d_out, c->d_stage_params[STAGE], nl, c->v_begin, scale);
+    }
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    // OpenBLAS' 1-row remainder kernel: last vertex of an odd-sized graph (exact mode only)
+    if (mode == GVC_MODE_EXACT && (c->n_global & 1u) && c->v_end == c->n_global) {
+        stage_tail_kernel<STAGE><<<1, 32, 0, c->stream>>>(c->row_ptr, c->col, c->Wv, c->NWv, d_in, d_out,
+                                                          c->d_stage_params[STAGE], nl - 1, c->v_begin, scale);
+        GVC_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+template <int STAGE>
+int set_stage_attrs() {
+    const int smem = (int)stage_smem_bytes<STAGE>();
+    GVC_CUDA(cudaFuncSetAttribute(stage_kernel<STAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GVC_CUDA(cudaFuncSetAttribute(stage_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return 0;
+}
+
+int check_ctx(const gvc_ctx *c) {
+    if (!c) return fail(GVC_ERR_ARG, "null context");
+    return 0;
+}
+
+int use_device(const gvc_ctx *c) {
+    GVC_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+int ensure_activations(gvc_ctx *c) {
+    int rc;
+    if ((rc = c->d_x.reserve(c->n_global))) return rc;
+    if ((rc = c->d_h1.reserve((size_t)c->n_global * 16))) return rc;
+    if ((rc = c->d_h2.reserve((size_t)c->n_global * 16))) return rc;
+    if ((rc = c->d_scores.reserve(c->n_local()))) return rc;
+    return 0;
+}
+
+// generic path: any layer sequence, single shard
+int forward_generic(gvc_ctx *c, const float *d_x, float scale, float *d_scores, int mode) {
+    const uint32_t n = c->n_global;
+    int w = 1, maxw = 1;
+    for (auto &l : c->layers) {
+        if (l.kind == GVC_LINEAR) w = l.cols;
+        else if (l.kind == GVC_GRAPH) w = 2 * w + 3;
+        if (w > maxw) maxw = w;
+    }
+    if (w != 1) return fail(GVC_ERR_UNSUPPORTED, "model output width %d != 1", w);
+    int rc;
+    if ((rc = c->d_ping.reserve((size_t)n * maxw))) return rc;
+    if ((rc = c->d_pong.reserve((size_t)n * maxw))) return rc;
+    const float *cur = d_x;
+    float *bufs[2] = {c->d_ping.p, c->d_pong.p};
+    int which = 0;
+    w = 1;
+    const int T = 256;
+    for (size_t li = 0; li < c->layers.size(); ++li) {
+        auto &l = c->layers[li];
+        const bool last = li + 1 == c->layers.size();
+        float *dst = last ? d_scores : bufs[which];
+        int wo = w;
+        switch (l.kind) {
+        case GVC_LINEAR:
+            if (l.rows != w) return fail(GVC_ERR_ARG, "layer %zu expects width %d, got %d", li, l.rows, w);
+            wo = l.cols;
+            if (mode == GVC_MODE_EXACT)
+                generic_linear_kernel<true><<<blocks_for((uint64_t)n * wo, T), T, 0, c->stream>>>(cur, l.rows, l.cols, l.dW, l.db, dst, n);
+            else
+                generic_linear_kernel<false><<<blocks_for((uint64_t)n * wo, T), T, 0, c->stream>>>(cur, l.rows, l.cols, l.dW, l.db, dst, n);
+            break;
+        case GVC_GRAPH:
+            wo = 2 * w + 3;
+            generic_graph_kernel<<<blocks_for((uint64_t)n * wo, T), T, 0, c->stream>>>(c->row_ptr, c->col, c->Wv, c->NWv, cur, w, dst, n, 0, scale);
+            break;
+        case GVC_RELU:
+            generic_relu_kernel<<<blocks_for((uint64_t)n * w, T), T, 0, c->stream>>>(cur, dst, (uint64_t)n * w);
+            break;
+        default:
+            if (mode == GVC_MODE_EXACT)
+                generic_sigmoid_kernel<true><<<blocks_for((uint64_t)n * w, T), T, 0, c->stream>>>(cur, dst, (uint64_t)n * w);
+            else
+                generic_sigmoid_kernel<false><<<blocks_for((uint64_t)n * w, T), T, 0, c->stream>>>(cur, dst, (uint64_t)n * w);
+            break;
+        }
+        GVC_CUDA(cudaGetLastError());
+        c->launches++;
+        cur = dst;
+        which ^= 1;
+        w = wo;
+    }
+    return 0;
+}
+
+int set_graph_views(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_end, const uint32_t *rp,
+                    const uint32_t *col, const uint32_t *W, const uint32_t *NW, uint64_t nnz) {
+    c->n_global = n_global; c->v_begin = v_begin; c->v_end = v_end; c->nnz = nnz;
+    c->row_ptr = rp; c->col = col; c->Wv = W; c->NWv = NW;
+    c->have_graph = true;
+    return ensure_activations(c);
+}
+
+}  // namespace
+
+// ================================ C ABI ==========================================
+extern "C" {
+
+const char *gvc_last_error(void) { return g_err.c_str(); }
+int gvc_abi_version(void) { return 1; }
+
+int gvc_ctx_create(gvc_ctx **out, int device) {
+    if (!out) return fail(GVC_ERR_ARG, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(GVC_ERR_NO_DEVICE, "no CUDA device: %s (libgvc has no CPU path)", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(GVC_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    GVC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GVC_ERR_NO_DEVICE, "device %d is sm_%d%d; libgvc is built for sm_100a only", device, prop.major, prop.minor);
+    gvc_ctx *c = new (std::nothrow) gvc_ctx();
+    if (!c) return fail(GVC_ERR_ALLOC, "out of host memory");
+    c->device = device;
+    GVC_CUDA(cudaSetDevice(device));
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(1000 + (int)e, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    int rc;
+    if ((rc = set_stage_attrs<0>()) || (rc = set_stage_attrs<1>()) || (rc = set_stage_attrs<2>())) {
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+void gvc_ctx_destroy(gvc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &l : c->layers) { if (l.dW) cudaFree(l.dW); if (l.db) cudaFree(l.db); }
+    for (auto &p : c->d_stage_params) if (p) cudaFree(p);
+    c->own_row_ptr.release(); c->own_col.release(); c->own_W.release(); c->own_NW.release();
+    c->stage_u32.release();
+    c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
+    c->d_ping.release(); c->d_pong.release();
+    c->pin_x.release(); c->pin_scores.release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int gvc_model_upload(gvc_ctx *c, int n_layers, const int *kinds, const int *rows, const int *cols,
+                     const float *const *W, const float *const *bias) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (n_layers <= 0 || !kinds) return fail(GVC_ERR_ARG, "empty model");   // assert(!layers.empty()), :68
+    if ((rc = use_device(c))) return rc;
+    for (auto &l : c->layers) { if (l.dW) cudaFree(l.dW); if (l.db) cudaFree(l.db); }
+    c->layers.clear();
+    for (auto &p : c->d_stage_params) { if (p) cudaFree(p); p = nullptr; }
+    c->layers.resize(n_layers);
+    for (int i = 0; i < n_layers; ++i) {
+        HostLayer &l = c->layers[i];
+        l.kind = kinds[i];
+        if (l.kind < GVC_LINEAR || l.kind > GVC_SIGMOID) return fail(GVC_ERR_ARG, "layer %d: unknown kind %d", i, l.kind);
+        if (l.kind != GVC_LINEAR) continue;
+        if (!rows || !cols || !W || !bias || !W[i] || !bias[i] || rows[i] <= 0 || cols[i] <= 0)
+            return fail(GVC_ERR_ARG, "layer %d: linear layer needs rows, cols, W and bias", i);
+        l.rows = rows[i]; l.cols = cols[i];
+        l.W.assign(W[i], W[i] + (size_t)l.rows * l.cols);
+        l.b.assign(bias[i], bias[i] + l.cols);
+        GVC_CUDA(cudaMalloc(&l.dW, l.W.size() * sizeof(float)));
+        GVC_CUDA(cudaMalloc(&l.db, l.b.size() * sizeof(float)));
+        GVC_CUDA(cudaMemcpyAsync(l.dW, l.W.data(), l.W.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        GVC_CUDA(cudaMemcpyAsync(l.db, l.b.data(), l.b.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    c->fused = detect_fused(c->layers);
+    if (c->fused) {
+        for (int s = 0; s < 3; ++s) {
+            std::vector<float> p = pack_stage(c->layers, s);
+            GVC_CUDA(cudaMalloc(&c->d_stage_params[s], p.size() * sizeof(float)));
+            GVC_CUDA(cudaMemcpy(c->d_stage_params[s], p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    }
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gvc_model_is_fused(const gvc_ctx *c) { return c && c->fused ? 1 : 0; }
+
+int gvc_graph_upload_shard(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_end,
+                           const uint64_t *row_ptr, const uint32_t *col, const uint32_t *W,
+                           const uint32_t *NW) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (v_begin > v_end || v_end > n_global) return fail(GVC_ERR_ARG, "bad shard [%u,%u) of %u", v_begin, v_end, n_global);
+    const uint32_t nl = v_end - v_begin;
+    if (nl && (!row_ptr || !W || !NW)) return fail(GVC_ERR_ARG, "null graph arrays");
+    if ((rc = use_device(c))) return rc;
+    const uint64_t nnz = nl ? row_ptr[nl] : 0;
+    if (nl && row_ptr[0] != 0) return fail(GVC_ERR_ARG, "row_ptr[0] must be 0");
+    if (nnz >= (1ull << 32)) return fail(GVC_ERR_UNSUPPORTED, "shard has %llu adjacency entries; 2^32 is the limit", (unsigned long long)nnz);
+    if (nnz && !col) return fail(GVC_ERR_ARG, "null col");
+    if ((rc = c->own_row_ptr.reserve((size_t)nl + 1))) return rc;
+    if ((rc = c->own_col.reserve(nnz))) return rc;
+    if ((rc = c->own_W.reserve(nl))) return rc;
+    if ((rc = c->own_NW.reserve(nl))) return rc;
+    // narrow the 64-bit offsets to the 32-bit layout the kernels read (pinned staging)
+    if ((rc = c->stage_u32.reserve((size_t)nl + 1))) return rc;
+    c->stage_u32.p[0] = 0;
+    for (uint32_t u = 0; u < nl; ++u) {
+        if (row_ptr[u + 1] < row_ptr[u]) return fail(GVC_ERR_ARG, "row_ptr not monotone at %u", u);
+        c->stage_u32.p[u + 1] = (uint32_t)row_ptr[u + 1];
+    }
+    GVC_CUDA(cudaMemcpyAsync(c->own_row_ptr.p, c->stage_u32.p, ((size_t)nl + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    if (nnz) GVC_CUDA(cudaMemcpyAsync(c->own_col.p, col, nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    if (nl) {
+        GVC_CUDA(cudaMemcpyAsync(c->own_W.p, W, (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
+        GVC_CUDA(cudaMemcpyAsync(c->own_NW.p, NW, (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    return set_graph_views(c, n_global, v_begin, v_end, c->own_row_ptr.p, c->own_col.p, c->own_W.p, c->own_NW.p, nnz);
+}
+
+int gvc_graph_upload(gvc_ctx *c, uint32_t n, const uint64_t *row_ptr, const uint32_t *col,
+                     const uint32_t *W, const uint32_t *NW) {
+    return gvc_graph_upload_shard(c, n, 0, n, row_ptr, col, W, NW);
+}
+
+int gvc_graph_adopt_device(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_end,
+                           const uint32_t *d_row_ptr, const uint32_t *d_col, const uint32_t *d_W,
+                           const uint32_t *d_NW) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (v_begin > v_end || v_end > n_global) return fail(GVC_ERR_ARG, "bad shard [%u,%u) of %u", v_begin, v_end, n_global);
+    if (v_end > v_begin && (!d_row_ptr || !d_W || !d_NW)) return fail(GVC_ERR_ARG, "null graph arrays");
+    if ((rc = use_device(c))) return rc;
+    return set_graph_views(c, n_global, v_begin, v_end, d_row_ptr, d_col, d_W, d_NW, 0);
+}
+
+int gvc_stage_device(gvc_ctx *c, int stage, const float *d_in, float *d_out, float scale, int mode) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!c->fused) return fail(GVC_ERR_STATE, "stage kernels need the GNN_VC architecture (model not uploaded or not fused)");
+    if (!c->have_graph) return fail(GVC_ERR_STATE, "no graph uploaded");
+    if (mode != GVC_MODE_EXACT && mode != GVC_MODE_FAST) return fail(GVC_ERR_ARG, "bad mode %d", mode);
+    if (c->n_local() && (!d_in || !d_out)) return fail(GVC_ERR_ARG, "null buffer");
+    if ((rc = use_device(c))) return rc;
+    switch (stage) {
+    case 0: return launch_stage<0>(c, d_in, d_out, scale, mode);
+    case 1: return launch_stage<1>(c, d_in, d_out, scale, mode);
+    case 2: return launch_stage<2>(c, d_in, d_out, scale, mode);
+    default: return fail(GVC_ERR_ARG, "stage %d out of range", stage);
+    }
+}
+
+int gvc_forward_device(gvc_ctx *c, const float *d_x, float scale, float *d_scores, int mode) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (c->layers.empty()) return fail(GVC_ERR_STATE, "no model uploaded");
+    if (!c->have_graph) return fail(GVC_ERR_STATE, "no graph uploaded");
+    if (c->v_begin != 0 || c->v_end != c->n_global)
+        return fail(GVC_ERR_STATE, "gvc_forward_device needs a whole-graph context; shards go through gvc_stage_device");
+    if (mode != GVC_MODE_EXACT && mode != GVC_MODE_FAST) return fail(GVC_ERR_ARG, "bad mode %d", mode);
+    if (c->n_global == 0) return 0;   // predict on an empty graph is a no-op
+    if (!d_x || !d_scores) return fail(GVC_ERR_ARG, "null buffer");
+    if ((rc = use_device(c))) return rc;
+    if (!c->fused) return forward_generic(c, d_x, scale, d_scores, mode);
+    if ((rc = launch_stage<0>(c, d_x, c->d_h1.p, scale, mode))) return rc;
+    if ((rc = launch_stage<1>(c, c->d_h1.p, c->d_h2.p, scale, mode))) return rc;
+    return launch_stage<2>(c, c->d_h2.p, d_scores, scale, mode);
+}
+
+int gvc_forward(gvc_ctx *c, const float *x, float scale, float *scores, int mode) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!c->have_graph) return fail(GVC_ERR_STATE, "no graph uploaded");
+    const uint32_t n = c->n_global;
+    if (n == 0) return 0;
+    if (!x || !scores) return fail(GVC_ERR_ARG, "null buffer");
+    if ((rc = use_device(c))) return rc;
+    if ((rc = c->pin_x.reserve(n))) return rc;
+    if ((rc = c->pin_scores.reserve(n))) return rc;
+    std::memcpy(c->pin_x.p, x, (size_t)n * sizeof(float));
+    GVC_CUDA(cudaMemcpyAsync(c->d_x.p, c->pin_x.p, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = gvc_forward_device(c, c->d_x.p, scale, c->d_scores.p, mode))) return rc;
+    GVC_CUDA(cudaMemcpyAsync(c->pin_scores.p, c->d_scores.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    std::memcpy(scores, c->pin_scores.p, (size_t)n * sizeof(float));
+    return 0;
+}
+
+int gvc_graph_layer_device(gvc_ctx *c, const float *d_in, int width, float *d_out, float scale) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!c->have_graph) return fail(GVC_ERR_STATE, "no graph uploaded");
+    if (width <= 0) return fail(GVC_ERR_ARG, "width must be positive");
+    if ((rc = use_device(c))) return rc;
+    const uint32_t nl = c->n_local();
+    if (!nl) return 0;
+    const uint64_t work = (uint64_t)nl * (2 * width + 3);
+    generic_graph_kernel<<<blocks_for(work, 256), 256, 0, c->stream>>>(c->row_ptr, c->col, c->Wv, c->NWv, d_in, width,
+                                                                       d_out, nl, c->v_begin, scale);
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int gvc_linear_layer_device(gvc_ctx *c, int layer_index, uint64_t n, const float *d_in, float *d_out) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (layer_index < 0 || layer_index >= (int)c->layers.size() || c->layers[layer_index].kind != GVC_LINEAR)
+        return fail(GVC_ERR_ARG, "layer %d is not a linear layer", layer_index);
+    if ((rc = use_device(c))) return rc;
+    if (!n) return 0;
+    auto &l = c->layers[layer_index];
+    generic_linear_kernel<true><<<blocks_for(n * l.cols, 256), 256, 0, c->stream>>>(d_in, l.rows, l.cols, l.dW, l.db, d_out, n);
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int gvc_relu_device(gvc_ctx *c, uint64_t count, const float *d_in, float *d_out) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if ((rc = use_device(c))) return rc;
+    if (!count) return 0;
+    generic_relu_kernel<<<blocks_for(count, 256), 256, 0, c->stream>>>(d_in, d_out, count);
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int gvc_sigmoid_device(gvc_ctx *c, uint64_t count, const float *d_in, float *d_out, int mode) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if ((rc = use_device(c))) return rc;
+    if (!count) return 0;
+    if (mode == GVC_MODE_EXACT)
+        generic_sigmoid_kernel<true><<<blocks_for(count, 256), 256, 0, c->stream>>>(d_in, d_out, count);
+    else
+        generic_sigmoid_kernel<false><<<blocks_for(count, 256), 256, 0, c->stream>>>(d_in, d_out, count);
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+// ---- host-buffer single layers ------------------------------------------------------
+namespace {
+struct Scratch2 {   // two device scratch areas for the host-buffer layer calls
+    float *a = nullptr, *b = nullptr;
+};
+int host_io_begin(gvc_ctx *c, size_t in_floats, size_t out_floats, const float *in, Scratch2 *s) {
+    int rc;
+    if ((rc = c->d_ping.reserve(in_floats))) return rc;
+    if ((rc = c->d_pong.reserve(out_floats))) return rc;
+    s->a = c->d_ping.p; s->b = c->d_pong.p;
+    if (in_floats) GVC_CUDA(cudaMemcpyAsync(s->a, in, in_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+int host_io_end(gvc_ctx *c, size_t out_floats, float *out, const Scratch2 &s) {
+    if (out_floats) GVC_CUDA(cudaMemcpyAsync(out, s.b, out_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+}  // namespace
+
+int gvc_graph_layer_host(gvc_ctx *c, const float *in, int width, float *out, float scale) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!c->have_graph) return fail(GVC_ERR_STATE, "no graph uploaded");
+    if (c->v_begin != 0 || c->v_end != c->n_global) return fail(GVC_ERR_STATE, "whole-graph context required");
+    if (width <= 0) return fail(GVC_ERR_ARG, "width must be positive");
+    const size_t n = c->n_global;
+    if (!n) return 0;
+    if (!in || !out) return fail(GVC_ERR_ARG, "null buffer");
+    if ((rc = use_device(c))) return rc;
+    Scratch2 s;
+    if ((rc = host_io_begin(c, n * width, n * (2 * (size_t)width + 3), in, &s))) return rc;
+    if ((rc = gvc_graph_layer_device(c, s.a, width, s.b, scale))) return rc;
+    return host_io_end(c, n * (2 * (size_t)width + 3), out, s);
+}
+
+int gvc_linear_host(gvc_ctx *c, uint64_t n, int K, int Nout, const float *in, const float *W,
+                    const float *bias, float *out, int mode) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (K <= 0 || Nout <= 0) return fail(GVC_ERR_ARG, "bad layer shape %d x %d", K, Nout);
+    if (mode != GVC_MODE_EXACT && mode != GVC_MODE_FAST) return fail(GVC_ERR_ARG, "bad mode %d", mode);
+    if (!n) return 0;
+    if (!in || !W || !bias || !out) return fail(GVC_ERR_ARG, "null buffer");
+    if ((rc = use_device(c))) return rc;
+    Scratch2 s;
+    const size_t wf = (size_t)K * Nout + Nout;
+    if ((rc = host_io_begin(c, n * K + wf, n * Nout, in, &s))) return rc;
+    float *dW = s.a + n * K, *db = dW + (size_t)K * Nout;
+    GVC_CUDA(cudaMemcpyAsync(dW, W, (size_t)K * Nout * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    GVC_CUDA(cudaMemcpyAsync(db, bias, (size_t)Nout * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (mode == GVC_MODE_EXACT)
+        generic_linear_kernel<true><<<blocks_for(n * Nout, 256), 256, 0, c->stream>>>(s.a, K, Nout, dW, db, s.b, n);
+    else
+        generic_linear_kernel<false><<<blocks_for(n * Nout, 256), 256, 0, c->stream>>>(s.a, K, Nout, dW, db, s.b, n);
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    return host_io_end(c, n * Nout, out, s);
+}
+
+int gvc_relu_host(gvc_ctx *c, uint64_t count, const float *in, float *out) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!count) return 0;
+    if (!in || !out) return fail(GVC_ERR_ARG, "null buffer");
+    if ((rc = use_device(c))) return rc;
+    Scratch2 s;
+    if ((rc = host_io_begin(c, count, count, in, &s))) return rc;
+    if ((rc = gvc_relu_device(c, count, s.a, s.b))) return rc;
+    return host_io_end(c, count, out, s);
+}
+
+int gvc_sigmoid_host(gvc_ctx *c, uint64_t count, const float *in, float *out, int mode) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (mode != GVC_MODE_EXACT && mode != GVC_MODE_FAST) return fail(GVC_ERR_ARG, "bad mode %d", mode);
+    if (!count) return 0;
+    if (!in || !out) return fail(GVC_ERR_ARG, "null buffer");
+    if ((rc = use_device(c))) return rc;
+    Scratch2 s;
+    if ((rc = host_io_begin(c, count, count, in, &s))) return rc;
+    if ((rc = gvc_sigmoid_device(c, count, s.a, s.b, mode))) return rc;
+    return host_io_end(c, count, out, s);
+}
+
+int gvc_sgemm_host(gvc_ctx *c, int ta, int tb, uint64_t m, uint64_t n, uint64_t k, const float *A,
+                   uint64_t lda, const float *B, uint64_t ldb, float beta, float *Cm, uint64_t ldc) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!m || !n) return 0;
+    if ((k && (!A || !B)) || !Cm) return fail(GVC_ERR_ARG, "null buffer");
+    if ((rc = use_device(c))) return rc;
+    const size_t a_floats = (ta ? k : m) * lda, b_floats = (tb ? n : k) * ldb, c_floats = m * ldc;
+    if ((rc = c->d_ping.reserve(a_floats + b_floats))) return rc;
+    if ((rc = c->d_pong.reserve(c_floats))) return rc;
+    float *dA = c->d_ping.p, *dB = dA + a_floats, *dC = c->d_pong.p;
+    if (a_floats) GVC_CUDA(cudaMemcpyAsync(dA, A, a_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (b_floats) GVC_CUDA(cudaMemcpyAsync(dB, B, b_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (beta != 0.0f) GVC_CUDA(cudaMemcpyAsync(dC, Cm, c_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    generic_sgemm_kernel<<<blocks_for(m * n, 256), 256, 0, c->stream>>>(ta, tb, m, n, k, dA, lda, dB, ldb, beta, dC, ldc);
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    GVC_CUDA(cudaMemcpyAsync(Cm, dC, c_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void *gvc_stream(gvc_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int gvc_sync(gvc_ctx *c) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+uint64_t gvc_launch_count(const gvc_ctx *c) { return c ? c->launches : 0; }
+
+const float *gvc_debug_h(const gvc_ctx *c, int which) {
+    if (!c) return nullptr;
+    return which == 0 ? c->d_h1.p : c->d_h2.p;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+"""Vertex-range sharding of the forward over several GPUs, one process per GPU.
+
+SURVEY.md 8(e): contiguous vertex ranges with balanced work, every shard keeps the
+CSR rows of its range with GLOBAL neighbour ids; ``x`` is replicated, so stage 0
+needs no exchange; after stages 0 and 1 every rank publishes its 16-float rows
+and receives everybody else's (the graphs of interest are expander-like, nearly
+every remote row is referenced, so the exchange is an all-gather of row slices).
+Per-vertex arithmetic does not depend on the sharding, hence P-GPU scores equal
+1-GPU scores bit for bit.
+
+``torch.distributed`` is the plumbing (NCCL over NVLink on GPUs, gloo in the CPU
+tests); the compute is ``Context.stage_device`` (libgvc).  The stage function is
+a parameter so that the host logic here can be tested on CPU ranks.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class Shard:
+    """What one rank owns: rows [v_begin, v_end) of the global graph."""
+    n_global: int
+    v_begin: int
+    v_end: int
+    bounds: list            # parts + 1 boundaries, the same on every rank
+    row_ptr: torch.Tensor   # int32/int64 [n_local + 1], starts at 0
+    col: torch.Tensor       # int32 [nnz_local], global ids
+    weights: torch.Tensor   # int32 [n_local]
+    nw: torch.Tensor        # int32 [n_local]
+
+    @property
+    def n_local(self) -> int:
+        return self.v_end - self.v_begin
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+
+def make_shard(g, bounds, rank: int) -> Shard:
+    """Cut rank's vertex range out of a whole graph (graphs.Graph) that lives on any device."""
+    a, b = bounds[rank], bounds[rank + 1]
+    lo, hi = int(g.row_ptr[a].item()), int(g.row_ptr[b].item())
+    return Shard(n_global=g.n, v_begin=a, v_end=b, bounds=list(bounds),
+                 row_ptr=(g.row_ptr[a:b + 1] - lo).contiguous(),
+                 col=g.col[lo:hi].contiguous(), weights=g.weights[a:b].contiguous(),
+                 nw=g.nw[a:b].contiguous())
+
+
+def exchange_rows(full: torch.Tensor, bounds, group=None) -> None:
+    """All-gather of row slices, in place: on entry ``full[bounds[r]:bounds[r+1]]`` is valid on
+    rank r; on return every rank holds all rows.  Slices may differ in length."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    rank = dist.get_rank(group)
+    views = [full[bounds[r]:bounds[r + 1]] for r in range(world)]
+    dist.all_gather(views, views[rank], group=group)
+
+
+def sharded_forward(stage_fn, shard: Shard, x_full: torch.Tensor, h1: torch.Tensor, h2: torch.Tensor,
+                    scores_local: torch.Tensor, weight_scale: float, mode: int, group=None,
+                    before_exchange=None) -> None:
+    """The three stages with the two row exchanges between them.
+
+    stage_fn(stage, d_in, d_out, weight_scale, mode) enqueues one fused stage for this rank's
+    shard (``Context.stage_device``).  ``before_exchange()`` must make the stage's output
+    visible to the communication stream (stream sync for CUDA; nothing on CPU)."""
+    stage_fn(0, x_full, h1, weight_scale, mode)
+    if before_exchange:
+        before_exchange()
+    exchange_rows(h1, shard.bounds, group)
+    stage_fn(1, h1, h2, weight_scale, mode)
+    if before_exchange:
+        before_exchange()
+    exchange_rows(h2, shard.bounds, group)
+    stage_fn(2, h2, scores_local, weight_scale, mode)
+
+
+def gather_scores(scores_local: torch.Tensor, bounds, group=None) -> torch.Tensor:
+    """Concatenate the per-rank score slices on every rank (used by tests and the e2e read-back)."""
+    world = dist.get_world_size(group)
+    n = bounds[-1]
+    full = torch.empty(n, dtype=scores_local.dtype, device=scores_local.device)
+    full[bounds[dist.get_rank(group)]:bounds[dist.get_rank(group) + 1]] = scores_local
+    if world > 1:
+        exchange_rows(full, bounds, group)
+    return full

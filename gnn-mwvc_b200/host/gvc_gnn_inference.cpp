@@ -1,0 +1,248 @@
+// gvc_gnn_inference.cpp -- drop-in translation unit for the reference's
+// src/gnn_inference.cpp.
+//
+// Compiled against the reference's own, untouched include/gnn_inference.hpp: every
+// symbol declared there (include/gnn_inference.hpp:11-59) is defined here with
+// the same meaning, so src/GNN_VC.cpp (model parse :263, set_weight_scale :278,
+// predict :192) links and runs unchanged -- with the forward pass on a B200.
+//
+//   model::predict      -> CSR view of the reduction_graph through its public
+//                          accessors, then gvc_graph_upload + gvc_forward
+//   layer ::forward     -> the matching single-layer entry points of libgvc
+//   parse / print / add -> host code, same text format
+//
+// No OpenBLAS, no CPU arithmetic: a missing GPU is a fatal error.
+#include "gnn_inference.hpp"
+
+#include <cmath>
+#include <cstdint>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "gvc.h"
+#include "gvc_host_ctx.hpp"
+
+using namespace gnn;
+
+namespace {
+
+const float *cdata(const matrix &m) { return m.get_height() * m.get_width() ? &m(0, 0) : nullptr; }
+float *mdata(matrix &m) { return m.get_height() * m.get_width() ? &m(0, 0) : nullptr; }
+
+// Host-side CSR scratch, reused between predict calls (the graph shrinks).
+struct csr_scratch {
+    std::vector<uint64_t> row_ptr;
+    std::vector<uint32_t> col, w, nw;
+};
+
+csr_scratch &scratch() {
+    static csr_scratch s;
+    return s;
+}
+
+// What predict reads from the graph: size(), begin(u)/end(u), W(u), NW(u)
+// (reference src/gnn_inference.cpp:32-40).  D(u) is end(u)-begin(u): calling g.D(u)
+// would write the graph's mutable cursor (include/reduction_graph.hpp:144,240-245).
+// The ranges have holes and the raw edge array is much longer than the live
+// adjacency, so rows are compacted here, never uploaded raw.
+void extract_csr(const reduction_graph<Tn, Tw> &g, csr_scratch &s) {
+    const Tn n = g.size();
+    s.row_ptr.resize((size_t)n + 1);
+    s.w.resize(n);
+    s.nw.resize(n);
+    uint64_t total = 0;
+    for (Tn u = 0; u < n; ++u) {
+        s.row_ptr[u] = total;
+        total += (uint64_t)(g.end(u) - g.begin(u));
+    }
+    s.row_ptr[n] = total;
+    s.col.resize(total);
+    for (Tn u = 0; u < n; ++u) {
+        std::copy(g.begin(u), g.end(u), s.col.begin() + s.row_ptr[u]);
+        s.w[u] = g.W(u);
+        s.nw[u] = g.NW(u);
+    }
+}
+
+// Fingerprint of a model's layers, to know when the device copy is stale.
+struct model_key {
+    const void *owner = nullptr;
+    uint64_t hash = 0;
+};
+
+uint64_t fnv(uint64_t h, const void *p, size_t bytes) {
+    const unsigned char *b = static_cast<const unsigned char *>(p);
+    for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+template <class... Ts>
+struct visitor : Ts... { using Ts::operator()...; };
+template <class... Ts>
+visitor(Ts...) -> visitor<Ts...>;
+
+int kind_of(const component &c) {
+    return std::visit(visitor{[](const linear_layer &) { return (int)GVC_LINEAR; },
+                              [](const graph_layer &) { return (int)GVC_GRAPH; },
+                              [](const ReLU &) { return (int)GVC_RELU; },
+                              [](const sigmoid &) { return (int)GVC_SIGMOID; }},
+                      c);
+}
+
+void upload_model_if_stale(gvc_ctx *ctx, const void *owner, const std::vector<component> &layers) {
+    static model_key current;
+    uint64_t h = 1469598103934665603ull;
+    for (auto &c : layers) {
+        const int k = kind_of(c);
+        h = fnv(h, &k, sizeof(k));
+        if (auto *l = std::get_if<linear_layer>(&c)) {
+            const size_t r = l->W.get_height(), cc = l->W.get_width();
+            h = fnv(h, &r, sizeof(r));
+            h = fnv(h, &cc, sizeof(cc));
+            if (r * cc) h = fnv(h, cdata(l->W), r * cc * sizeof(float));
+            if (l->bias.get_width()) h = fnv(h, cdata(l->bias), l->bias.get_width() * sizeof(float));
+        }
+    }
+    if (current.owner == owner && current.hash == h) return;
+    const int n = (int)layers.size();
+    std::vector<int> kinds(n), rows(n, 0), cols(n, 0);
+    std::vector<const float *> W(n, nullptr), b(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        kinds[i] = kind_of(layers[i]);
+        if (auto *l = std::get_if<linear_layer>(&layers[i])) {
+            rows[i] = (int)l->W.get_height();
+            cols[i] = (int)l->W.get_width();
+            W[i] = cdata(l->W);
+            b[i] = cdata(l->bias);
+        }
+    }
+    const int rc = gvc_model_upload(ctx, n, kinds.data(), rows.data(), cols.data(), W.data(), b.data());
+    if (rc != 0) gvc_host::die("gvc_model_upload", rc);
+    current.owner = owner;
+    current.hash = h;
+}
+
+}  // namespace
+
+// ---- linear_layer (include/gnn_inference.hpp:11-17) ----------------------------------
+// Random init as the reference's ctor, src/gnn_inference.cpp:7-18: uniform in
+// +-1/sqrt(dim_in + 1) from mt19937(seed), weights first, then bias.
+linear_layer::linear_layer(size_t dim_in, size_t dim_out, size_t seed) : W(dim_in, dim_out), bias(1, dim_out) {
+    const float lim = 1.0 / sqrt(dim_in + 1);
+    std::mt19937 gen(seed);
+    std::uniform_real_distribution<float> dist(-lim, lim);
+    for (auto it = W.raw().begin(); it != W.raw().end(); ++it) *it = dist(gen);
+    for (auto it = bias.raw().begin(); it != bias.raw().end(); ++it) *it = dist(gen);
+}
+
+// out = in * W + bias (src/gnn_inference.cpp:20-25), on the GPU, reference operation order
+void linear_layer::forward(const matrix &in, matrix &out) const {
+    const size_t n = in.get_height();
+    out.resize(n, W.get_width());
+    if (n == 0 || W.get_width() == 0) return;
+    const int rc = gvc_linear_host(gvc_host::context(), n, (int)W.get_height(), (int)W.get_width(), cdata(in),
+                                   cdata(W), cdata(bias), mdata(out), gvc_host::mode());
+    if (rc != 0) gvc_host::die("gvc_linear_host", rc);
+}
+
+// ---- graph_layer (include/gnn_inference.hpp:24-28; src/gnn_inference.cpp:27-42) ---------
+void graph_layer::forward(const matrix &in, matrix &out, const reduction_graph<Tn, Tw> &g) const {
+    const size_t n = in.get_height(), w = in.get_width();
+    out.resize(n, 2 * w + 3);
+    if (n == 0) return;
+    gvc_ctx *ctx = gvc_host::context();
+    csr_scratch &s = scratch();
+    extract_csr(g, s);
+    int rc = gvc_graph_upload(ctx, g.size(), s.row_ptr.data(), s.col.data(), s.w.data(), s.nw.data());
+    if (rc != 0) gvc_host::die("gvc_graph_upload", rc);
+    rc = gvc_graph_layer_host(ctx, cdata(in), (int)w, mdata(out), WEIGHT_SCALE);
+    if (rc != 0) gvc_host::die("gvc_graph_layer_host", rc);
+}
+
+// ---- activations (src/gnn_inference.cpp:44-52) -----------------------------------------
+void ReLU::forward(const matrix &in, matrix &out) const {
+    out.resize(in.get_height(), in.get_width());
+    const size_t count = in.get_height() * in.get_width();
+    if (!count) return;
+    const int rc = gvc_relu_host(gvc_host::context(), count, cdata(in), mdata(out));
+    if (rc != 0) gvc_host::die("gvc_relu_host", rc);
+}
+
+void sigmoid::forward(const matrix &in, matrix &out) const {
+    out.resize(in.get_height(), in.get_width());
+    const size_t count = in.get_height() * in.get_width();
+    if (!count) return;
+    const int rc = gvc_sigmoid_host(gvc_host::context(), count, cdata(in), mdata(out), gvc_host::mode());
+    if (rc != 0) gvc_host::die("gvc_sigmoid_host", rc);
+}
+
+// ---- model (include/gnn_inference.hpp:40-59) ----------------------------------------------
+model::model(std::string name) : name(name) {}
+
+void model::add_layer(const component &c) { layers.push_back(c); }
+
+void model::set_weight_scale(float ws) {   // src/gnn_inference.cpp:83-90
+    for (auto &c : layers)
+        if (auto *gl = std::get_if<graph_layer>(&c)) gl->WEIGHT_SCALE = ws;
+}
+
+// The hot path (src/gnn_inference.cpp:67-81).  `in` is left untouched, `out` becomes
+// N x 1; an empty graph is a no-op that still shapes `out`.
+void model::predict(const matrix &in, matrix &out, const reduction_graph<Tn, Tw> &g) const {
+    const Tn n = g.size();
+    out.resize(n, 1);
+    if (n == 0 || layers.empty()) return;
+    gvc_ctx *ctx = gvc_host::context();
+    upload_model_if_stale(ctx, this, layers);
+
+    float scale = 120.0f;   // graph_layer::WEIGHT_SCALE default, include/gnn_inference.hpp:25
+    for (auto &c : layers)
+        if (auto *gl = std::get_if<graph_layer>(&c)) { scale = gl->WEIGHT_SCALE; break; }
+
+    csr_scratch &s = scratch();
+    extract_csr(g, s);
+    int rc = gvc_graph_upload(ctx, n, s.row_ptr.data(), s.col.data(), s.w.data(), s.nw.data());
+    if (rc != 0) gvc_host::die("gvc_graph_upload", rc);
+    rc = gvc_forward(ctx, cdata(in), scale, mdata(out), gvc_host::mode());
+    if (rc != 0) gvc_host::die("gvc_forward", rc);
+}
+
+// ---- text format (src/gnn_inference.cpp:92-139) --------------------------------
+std::ostream &gnn::operator<<(std::ostream &os, const model &m) {
+    os << m.name << std::endl << m.layers.size() << " Layers" << std::endl;
+    for (auto &c : m.layers) {
+        switch (kind_of(c)) {
+        case GVC_LINEAR: {
+            const linear_layer &l = std::get<linear_layer>(c);
+            os << "Linear_Layer" << std::endl
+               << "Weights: " << l.W << std::endl
+               << "Bias: " << l.bias << std::endl;
+            break;
+        }
+        case GVC_GRAPH: os << "Graph_Layer" << std::endl; break;
+        case GVC_RELU: os << "ReLU_Activation" << std::endl; break;
+        default: os << "Sigmoid_Activation" << std::endl; break;
+        }
+        os << std::endl;
+    }
+    return os;
+}
+
+std::istream &gnn::operator>>(std::istream &is, model &m) {
+    size_t count = 0;
+    std::string word;
+    is >> m.name >> count >> word;                  // "<name> <n> Layers"
+    for (size_t i = 0; i < count && is; ++i) {
+        is >> word;
+        if (word == "Graph_Layer") m.layers.emplace_back(graph_layer());
+        else if (word == "ReLU_Activation") m.layers.emplace_back(ReLU());
+        else if (word == "Sigmoid_Activation") m.layers.emplace_back(sigmoid());
+        else if (word == "Linear_Layer") {
+            linear_layer l;
+            is >> word >> l.W >> word >> l.bias;    // "Weights:" matrix "Bias:" matrix
+            m.layers.emplace_back(std::move(l));
+        }                                           // anything else is skipped, as in the reference
+    }
+    return is;
+}

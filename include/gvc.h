@@ -1,0 +1,171 @@
+/*
+ * gvc.h -- C ABI of libgvc.so, the B200 (sm_100a) GNN forward for GNN_VC.
+ *
+ * This is the drop-in boundary for the hot path gnn::model::predict of the
+ * reference (KennethLangedal/GNN-MWVC).  Plain pointers and sizes only; no C++,
+ * torch or CUDA types.  The reference-side binding (a replacement
+ * src/gnn_inference.cpp that keeps include/gnn_inference.hpp untouched) lives in
+ * gnn-mwvc_b200/host/ and is described in INTEGRATION.md.
+ *
+ * Every entry point names the reference interface it stands in for
+ * (file:line under the reference tree).
+ *
+ * Conventions: all functions return 0 on success or a non-zero code and leave a
+ * message retrievable with gvc_last_error(); none of them throws or aborts.
+ * One context belongs to one CUDA device and one caller thread (the reference's
+ * predict is not re-entrant either: include/gnn_inference.hpp:44 `mutable`).
+ * There is no CPU fallback: without a usable CUDA device gvc_ctx_create fails.
+ */
+#ifndef GVC_H
+#define GVC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gvc_ctx gvc_ctx;
+
+/* Layer kinds, in the order of gnn::component's variant alternatives
+ * (include/gnn_inference.hpp:38). */
+enum { GVC_LINEAR = 0, GVC_GRAPH = 1, GVC_RELU = 2, GVC_SIGMOID = 3 };
+
+/* Arithmetic modes of the forward.
+ *  GVC_MODE_EXACT reproduces the reference's fp32 operation order (OpenBLAS
+ *    0.3.15 "Prescott" sgemm run single-threaded, sequential neighbour sums,
+ *    glibc expf): scores are bit-identical to the reference.
+ *  GVC_MODE_FAST uses fused multiply-adds and the device expf: scores agree to
+ *    1e-4 relative (typically ~1e-6), not bit for bit. */
+enum { GVC_MODE_EXACT = 0, GVC_MODE_FAST = 1 };
+
+/* Error codes (besides CUDA's own, passed through as 1000 + cudaError_t). */
+enum {
+    GVC_OK = 0,
+    GVC_ERR_ARG = 1,        /* bad argument */
+    GVC_ERR_STATE = 2,      /* model or graph not uploaded yet */
+    GVC_ERR_NO_DEVICE = 3,  /* no CUDA device / wrong architecture */
+    GVC_ERR_ALLOC = 4,
+    GVC_ERR_UNSUPPORTED = 5
+};
+
+const char *gvc_last_error(void);
+
+/* Version of this ABI (bumped on incompatible change). */
+int gvc_abi_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+
+/* One context per device; stands in for the gnn::model object's life time
+ * (src/GNN_VC.cpp:250).  `device` is a CUDA ordinal. */
+int gvc_ctx_create(gvc_ctx **out, int device);
+void gvc_ctx_destroy(gvc_ctx *ctx);
+
+/* ---- model: gnn::operator>> (src/gnn_inference.cpp:120-139) --------------- */
+
+/* Upload a parsed model: n_layers records; kinds[i] in GVC_*; for GVC_LINEAR
+ * rows[i] x cols[i] row-major weights W[i] and cols[i] bias values bias[i]
+ * (host pointers, copied; ignored for other kinds).  Any layer sequence the
+ * reference parser accepts is accepted.  The 21-layer GNN_VC architecture
+ *  is detected structurally and runs on the fused kernels; every
+ * other sequence runs on per-layer kernels. */
+int gvc_model_upload(gvc_ctx *ctx, int n_layers, const int *kinds, const int *rows,
+                     const int *cols, const float *const *W, const float *const *bias);
+
+/* 1 if the uploaded model runs on the fused three-kernel path, else 0. */
+int gvc_model_is_fused(const gvc_ctx *ctx);
+
+/* ---- graph: what predict reads through reduction_graph's accessors ---------
+ * size() include/reduction_graph.hpp:141, begin(u)/end(u) :692-704, D :144,
+ * W :147-151, NW :153-158, as used at src/gnn_inference.cpp:32-40.
+ *
+ * CSR with n vertices: row_ptr[n+1] (row_ptr[0] == 0), col[row_ptr[n]]
+ * 0-indexed neighbour ids in the order begin(u)..end(u) yields them, W[n] and
+ * NW[n] the integer vertex and neighbourhood weights.  Host pointers, copied. */
+int gvc_graph_upload(gvc_ctx *ctx, uint32_t n, const uint64_t *row_ptr, const uint32_t *col,
+                     const uint32_t *W, const uint32_t *NW);
+
+/* Vertex-range shard for multi-GPU runs (one process per GPU): this context
+ * owns vertices [v_begin, v_end) of an n_global-vertex graph.  row_ptr has
+ * v_end - v_begin + 1 entries starting at 0; col holds GLOBAL neighbour ids;
+ * W/NW are the shard's slices.  Host pointers, copied. */
+int gvc_graph_upload_shard(gvc_ctx *ctx, uint32_t n_global, uint32_t v_begin, uint32_t v_end,
+                           const uint64_t *row_ptr, const uint32_t *col, const uint32_t *W,
+                           const uint32_t *NW);
+
+/* Same shard description with DEVICE pointers that stay owned by the caller and
+ * must outlive the context's use of them (no copy; row_ptr is uint32 here, the
+ * layout the kernels read).  Used by the benchmark, which builds its synthetic
+ * graphs on the GPU. */
+int gvc_graph_adopt_device(gvc_ctx *ctx, uint32_t n_global, uint32_t v_begin, uint32_t v_end,
+                           const uint32_t *d_row_ptr, const uint32_t *d_col, const uint32_t *d_W,
+                           const uint32_t *d_NW);
+
+/* ---- forward: gnn::model::predict (src/gnn_inference.cpp:67-81) ------------ */
+
+/* Whole forward with HOST buffers: x[n] (= in(u,0), src/GNN_VC.cpp:189-191),
+ * weight_scale (= graph_layer::WEIGHT_SCALE, include/gnn_inference.hpp:25, set by
+ * set_weight_scale src/gnn_inference.cpp:83-90), scores[n] (= out(u,0)).  Includes
+ * the host->device copy of x and the device->host copy of the scores.  n == 0
+ * is a no-op (the reference is called with an empty graph).
+ * Single-shard contexts only. */
+int gvc_forward(gvc_ctx *ctx, const float *x, float weight_scale, float *scores, int mode);
+
+/* Same with DEVICE buffers (d_x[n_global], d_scores[v_end - v_begin]), enqueued
+ * on the context's stream without synchronising.  Single-shard contexts only. */
+int gvc_forward_device(gvc_ctx *ctx, const float *d_x, float weight_scale, float *d_scores,
+                       int mode);
+
+/* One fused stage of the GNN_VC architecture on this context's shard, DEVICE
+ * buffers, enqueued on the context's stream:
+ *   stage 0: graph layer (w=1)  + 5->32->32->16   d_in = x  [n_global]      -> d_out = h1 [n_global x 16]
+ *   stage 1: graph layer (w=16) + 35->32->32->16  d_in = h1 [n_global x 16] -> d_out = h2 [n_global x 16]
+ *   stage 2: graph layer (w=16) + 35->32->16->1 + sigmoid
+ *                                                 d_in = h2 [n_global x 16] -> d_out = scores [v_end - v_begin]
+ * Stages 0 and 1 write rows [v_begin, v_end) of the FULL d_out buffer; the
+ * caller exchanges the other rows between shards before the next stage
+ * (gnn-mwvc_b200/dist.py).  Reference: graph_layer::forward :27-42,
+ * linear_layer::forward :20-25, ReLU :44-47, sigmoid :49-52. */
+int gvc_stage_device(gvc_ctx *ctx, int stage, const float *d_in, float *d_out,
+                     float weight_scale, int mode);
+
+/* Single layers on device buffers, row counts explicit (generic path; also the
+ * kernel-level parity tests).  in/out are row-major n x width. */
+int gvc_graph_layer_device(gvc_ctx *ctx, const float *d_in, int width, float *d_out,
+                           float weight_scale);                       /* :27-42  */
+int gvc_linear_layer_device(gvc_ctx *ctx, int layer_index, uint64_t n, const float *d_in,
+                            float *d_out);                            /* :20-25  */
+int gvc_relu_device(gvc_ctx *ctx, uint64_t count, const float *d_in, float *d_out);      /* :44-47 */
+int gvc_sigmoid_device(gvc_ctx *ctx, uint64_t count, const float *d_in, float *d_out, int mode); /* :49-52 */
+
+/* Host-buffer forms of the single layers and of dot(): what the public
+ * forward() methods of the layer structs (include/gnn_inference.hpp:11-36) and
+ * dot (include/matrix.hpp:49, src/matrix.cpp:106-122) call in the drop-in host
+ * code.  Copies in, runs the kernel, copies out, synchronises. */
+int gvc_graph_layer_host(gvc_ctx *ctx, const float *in, int width, float *out, float weight_scale);
+int gvc_linear_host(gvc_ctx *ctx, uint64_t n, int K, int Nout, const float *in, const float *W,
+                    const float *bias, float *out, int mode);
+int gvc_relu_host(gvc_ctx *ctx, uint64_t count, const float *in, float *out);
+int gvc_sigmoid_host(gvc_ctx *ctx, uint64_t count, const float *in, float *out, int mode);
+/* Row-major C[m x n] = op(A) * op(B) + beta * C with op = transpose when the flag
+ * is non-zero; lda/ldb/ldc are the row lengths of the stored matrices. */
+int gvc_sgemm_host(gvc_ctx *ctx, int trans_a, int trans_b, uint64_t m, uint64_t n, uint64_t k,
+                   const float *A, uint64_t lda, const float *B, uint64_t ldb, float beta, float *C,
+                   uint64_t ldc);
+
+/* ---- plumbing ----------------------------------------------------------- */
+
+/* The context's CUDA stream as an opaque handle (cudaStream_t). */
+void *gvc_stream(gvc_ctx *ctx);
+/* Block until everything enqueued on the context's stream has finished. */
+int gvc_sync(gvc_ctx *ctx);
+/* Number of kernels this context has launched so far. */
+uint64_t gvc_launch_count(const gvc_ctx *ctx);
+/* Device buffers of the last forward (h1/h2: n_global x 16), for tests. */
+const float *gvc_debug_h(const gvc_ctx *ctx, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVC_H */

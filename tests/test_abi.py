@@ -1,0 +1,69 @@
+"""CPU: libgvc.so loads and exports every symbol include/gvc.h declares; without a GPU
+the product fails loudly (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+import gnn_mwvc_b200  # noqa: F401
+from gnn_mwvc_b200 import build, capi
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_libgvc()
+    return capi.load_library()
+
+
+def header_symbols():
+    text = (ROOT / "include" / "gvc.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gvc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"libgvc.so does not export {s}"
+    assert sorted(capi.SIGNATURES) == syms, "capi.SIGNATURES and include/gvc.h disagree"
+
+
+def test_built_for_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", str(capi.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_oracle_in_product():
+    """The product must not import, link or dlopen anything under oracle/."""
+    pkg = ROOT / "gnn-mwvc_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + \
+            list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.hpp")) + list(pkg.rglob("*.h")):
+        for line in p.read_text().splitlines():
+            code = line.split("//")[0].split("#", 1)[0] if p.suffix != ".py" else line.split("#", 1)[0]
+            if p.suffix != ".py" and line.lstrip().startswith("#include"):
+                code = line
+            uses = ("#include" in code and "oracle" in code) or re.search(r"\b(import|from)\s+oracle\b", code) \
+                or "libgnnref" in code or "libgnnoracle" in code
+            assert not uses, f"{p}: {line.strip()}"
+    ldd = subprocess.run(["ldd", str(capi.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "openblas" not in ldd.lower()
+
+
+def test_fails_loudly_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    h = C.c_void_p()
+    rc = lib.gvc_ctx_create(C.byref(h), 0)
+    assert rc != 0 and not h.value
+    assert b"no CUDA device" in lib.gvc_last_error() or b"CPU" in lib.gvc_last_error()
+    with pytest.raises(capi.GvcError):
+        capi.Context(0)
+
+
+def test_abi_version(lib):
+    assert lib.gvc_abi_version() == 1

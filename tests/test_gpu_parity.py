@@ -1,0 +1,261 @@
+"""GPU: the CUDA path, called through the C ABI (include/gvc.h), against the oracle and the
+committed golden vectors.  Exact mode is bit-for-bit; fast mode within the 1e-4 relative
+tolerance BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+import gnn_mwvc_b200 as pkg
+from gnn_mwvc_b200 import capi, graphs
+from helpers import (assert_bit_equal, assert_rel_close, golden_graph, golden_names, inputs_of,
+                     oracle_stages)
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+FAST_RTOL = 1e-4     # north_star: per-vertex scores within 1e-4 relative in fp32
+
+
+@pytest.fixture(scope="module")
+def ctx(model_layers):
+    c = pkg.Context(0)
+    c.model_upload(model_layers)
+    assert c.fused, "the GNN_VC architecture must take the fused path"
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def vec():
+    return np.load(GOLDEN / "predict_vectors.npz")
+
+
+@pytest.fixture(scope="module")
+def lay():
+    return np.load(GOLDEN / "layer_vectors.npz")
+
+
+def run(ctx, g, scale=None, mode=pkg.MODE_EXACT):
+    rp, col, W, NW, x, s = inputs_of(g, scale)
+    ctx.graph_upload(rp, col, W, NW)
+    return ctx.forward(x, s, mode)
+
+
+def test_golden_vectors_exact(ctx, vec):
+    for name in golden_names(vec):
+        g, s, want = golden_graph(vec, name)
+        assert_bit_equal(run(ctx, g, s), want, name)
+
+
+def test_golden_vectors_fast(ctx, vec):
+    for name in golden_names(vec):
+        g, s, want = golden_graph(vec, name)
+        assert_rel_close(run(ctx, g, s, pkg.MODE_FAST), want, FAST_RTOL, name)
+
+
+def test_known_answers(ctx, vec):
+    g, s, _ = golden_graph(vec, "readme")
+    np.testing.assert_allclose(run(ctx, g, s), [0.129362747, 0.129362747, 0.934816003], rtol=0, atol=5e-9)
+
+
+def test_empty_graph_is_noop(ctx):
+    z32, z64 = np.zeros(0, np.uint32), np.zeros(1, np.uint64)
+    ctx.graph_upload(z64, z32, z32, z32)
+    out = ctx.forward(np.zeros(0, np.float32), 20.0)
+    assert out.shape == (0,)
+
+
+@pytest.mark.parametrize("maker", [
+    lambda: graphs.er_graph(20001, 100000, seed=31),      # odd n: OpenBLAS 1-row tail
+    lambda: graphs.er_graph(9951, 49701, seed=32),        # first predict of the ER-10k run has n=9951
+    lambda: graphs.rmat_graph(15, 16, seed=33),           # hubs of degree ~10^3..10^4
+    lambda: graphs.grid_graph(150, 151, seed=34),
+    lambda: graphs.er_graph(33, 40, seed=35),             # a single partial tile
+    lambda: graphs.er_graph(257, 300, seed=36),           # one CTA + one vertex
+    lambda: graphs.graph_from_edges(64, torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64),
+                                    graphs.random_weights(64, 37)),   # all isolated
+])
+def test_forward_vs_oracle(ctx, oracle, oracle_model, maker):
+    g = maker()
+    rp, col, W, NW, x, s = inputs_of(g)
+    want = oracle.predict(oracle_model, rp, col, W, NW, x, s)[:, 0]
+    ctx.graph_upload(rp, col, W, NW)
+    assert_bit_equal(ctx.forward(x, s, pkg.MODE_EXACT), want, g.name)
+    assert_rel_close(ctx.forward(x, s, pkg.MODE_FAST), want, FAST_RTOL, g.name)
+    # identical downstream decision wherever the score is not within tolerance of 0.5
+    fast = ctx.forward(x, s, pkg.MODE_FAST)
+    clear = np.abs(want - 0.5) > 1e-4
+    assert np.array_equal((fast > 0.5)[clear], (want > 0.5)[clear])
+
+
+def test_stage_outputs_vs_oracle(ctx, oracle, model_layers):
+    g = graphs.rmat_graph(12, 16, seed=41, n_limit=4001)
+    rp, col, W, NW, x, s = inputs_of(g)
+    h1, h2, scores = oracle_stages(oracle, model_layers, rp, col, W, NW, x, s)
+    ctx.graph_upload(rp, col, W, NW)
+    dev = torch.device("cuda:0")
+    dx = torch.from_numpy(x).to(dev)
+    d1 = torch.empty(g.n, 16, device=dev)
+    d2 = torch.empty(g.n, 16, device=dev)
+    ds = torch.empty(g.n, device=dev)
+    torch.cuda.synchronize()
+    ctx.stage_device(0, dx, d1, s)
+    ctx.stage_device(1, d1, d2, s)
+    ctx.stage_device(2, d2, ds, s)
+    ctx.sync()
+    assert_bit_equal(d1.cpu().numpy(), h1, "h1")
+    assert_bit_equal(d2.cpu().numpy(), h2, "h2")
+    assert_bit_equal(ds.cpu().numpy(), scores, "scores")
+
+
+def test_weight_scale_and_x_are_honoured(ctx, oracle, oracle_model):
+    # predict must use the `in` it is given and the model's scale, not W/max(W)
+    g = graphs.er_graph(3000, 12000, seed=42)
+    rp, col, W, NW, _, _ = inputs_of(g)
+    x = np.random.default_rng(1).random(g.n).astype(np.float32) * 3
+    want = oracle.predict(oracle_model, rp, col, W, NW, x, 120.0)[:, 0]
+    ctx.graph_upload(rp, col, W, NW)
+    assert_bit_equal(ctx.forward(x, 120.0), want, "scale 120")
+
+
+def test_adjacency_order_is_respected(ctx, oracle, oracle_model):
+    # after folds the reference's adjacency is not ascending; sums follow the given order
+    g = graphs.er_graph(2000, 16000, seed=43)
+    rp, col, W, NW, x, s = inputs_of(g)
+    rng = np.random.default_rng(2)
+    col = col.copy()
+    for u in range(g.n):
+        rng.shuffle(col[int(rp[u]):int(rp[u + 1])])
+    want = oracle.predict(oracle_model, rp, col, W, NW, x, s)[:, 0]
+    ctx.graph_upload(rp, col, W, NW)
+    assert_bit_equal(ctx.forward(x, s), want, "shuffled adjacency")
+
+
+def test_graph_is_reuploaded_between_calls(ctx, oracle, oracle_model):
+    # GNN_VC calls predict on a shrinking graph 4-14 times with one model
+    for n, m, seed in ((5000, 20000, 51), (1500, 4000, 52), (301, 500, 53), (0, 0, 54), (77, 100, 55)):
+        g = graphs.er_graph(n, m, seed=seed) if n else None
+        if g is None:
+            z32, z64 = np.zeros(0, np.uint32), np.zeros(1, np.uint64)
+            ctx.graph_upload(z64, z32, z32, z32)
+            assert ctx.forward(np.zeros(0, np.float32), 200.0).size == 0
+            continue
+        rp, col, W, NW, x, s = inputs_of(g)
+        want = oracle.predict(oracle_model, rp, col, W, NW, x, s)[:, 0]
+        ctx.graph_upload(rp, col, W, NW)
+        assert_bit_equal(ctx.forward(x, s), want, g.name)
+
+
+def test_shards_are_bit_identical_to_one_gpu(ctx, model_layers):
+    """Vertex-range shards (the multi-GPU layout) emulated with several contexts on one GPU:
+    per-vertex arithmetic is unchanged, so P shards == 1 shard bit for bit."""
+    g = graphs.rmat_graph(13, 16, seed=61, n_limit=8191)
+    rp, col, W, NW, x, s = inputs_of(g)
+    ctx.graph_upload(rp, col, W, NW)
+    want = ctx.forward(x, s)
+    dev = torch.device("cuda:0")
+    for parts in (2, 3, 8):
+        bounds = graphs.nnz_balanced_ranges(g.row_ptr, parts)
+        shards = []
+        for p in range(parts):
+            a, b = bounds[p], bounds[p + 1]
+            c = pkg.Context(0)
+            c.model_upload(model_layers)
+            lo, hi = int(rp[a]), int(rp[b])
+            c.graph_upload(rp[a:b + 1] - rp[a], col[lo:hi], W[a:b], NW[a:b], n_global=g.n, v_begin=a, v_end=b)
+            shards.append(c)
+        dx = torch.from_numpy(x).to(dev)
+        d1 = torch.zeros(g.n, 16, device=dev)
+        d2 = torch.zeros(g.n, 16, device=dev)
+        outs = [torch.empty(bounds[p + 1] - bounds[p], device=dev) for p in range(parts)]
+        torch.cuda.synchronize()
+        for stage, (src, dst) in enumerate(((dx, d1), (d1, d2), (d2, None))):
+            for p, c in enumerate(shards):
+                c.stage_device(stage, src, dst if dst is not None else outs[p], s)
+            for c in shards:
+                c.sync()                      # the "exchange": every shard wrote its rows of the full buffer
+        got = torch.cat(outs).cpu().numpy()
+        assert_bit_equal(got, want, f"{parts} shards")
+        for c in shards:
+            c.close()
+
+
+def test_generic_path_any_layer_sequence(oracle):
+    """operator>> accepts any sequence of the four layer kinds; non-GNN_VC models run on
+    the per-layer kernels (SURVEY.md 8(b) genericity)."""
+    rng = np.random.default_rng(7)
+
+    def lin(K, N):
+        return (po.LINEAR, (rng.standard_normal((K, N)) * 0.4).astype(np.float32), rng.standard_normal(N).astype(np.float32) * 0.1)
+    layers = [(po.GRAPH, None, None), lin(5, 8), (po.RELU, None, None), (po.GRAPH, None, None), lin(19, 4),
+              (po.SIGMOID, None, None), lin(4, 1), (po.SIGMOID, None, None)]
+    c = pkg.Context(0)
+    c.model_upload(layers)
+    assert not c.fused
+    h = oracle.parse(po.layers_to_text(layers))
+    for g in (graphs.er_graph(1001, 4000, seed=71), graphs.er_graph(64, 100, seed=72)):
+        rp, col, W, NW, x, s = inputs_of(g)
+        want = oracle.predict(h, rp, col, W, NW, x, s)[:, 0]
+        c.graph_upload(rp, col, W, NW)
+        assert_bit_equal(c.forward(x, s), want, g.name)
+        assert_rel_close(c.forward(x, s, pkg.MODE_FAST), want, FAST_RTOL, g.name)
+    c.close()
+
+
+def test_single_layers_vs_golden(ctx, vec, lay):
+    """The layer structs' own forward() entry points (host-buffer ABI) against the reference's output."""
+    g, _, _ = golden_graph(vec, "readme")
+    rp, col, W, NW = g.numpy()
+    ctx.graph_upload(rp, col, W, NW)
+    assert_bit_equal(ctx.graph_layer_host(lay["graph16.in"], 20.0), lay["graph16.out"], "graph16")
+    g, _, _ = golden_graph(vec, "er607")
+    rp, col, W, NW = g.numpy()
+    ctx.graph_upload(rp, col, W, NW)
+    for w in (1, 16, 3):
+        assert_bit_equal(ctx.graph_layer_host(lay[f"graph_er607_w{w}.in"], 200.0), lay[f"graph_er607_w{w}.out"], f"w={w}")
+    for k in sorted(k[:-3] for k in lay.files if k.startswith("linear_") and k.endswith(".in")):
+        assert_bit_equal(ctx.linear_host(lay[k + ".in"], lay[k + ".W"], lay[k + ".b"]), lay[k + ".out"], k)
+    assert_bit_equal(ctx.relu_host(lay["relu.in"]), lay["relu.out"], "relu")
+    assert_bit_equal(ctx.sigmoid_host(lay["sigmoid.in"]), lay["sigmoid.out"], "sigmoid")
+    A = np.random.default_rng(3).standard_normal((7, 5)).astype(np.float32)
+    B = np.random.default_rng(4).standard_normal((5, 3)).astype(np.float32)
+    np.testing.assert_allclose(ctx.sgemm_host(A, B), A @ B, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ctx.sgemm_host(A.T.copy(), B, trans_a=True), A @ B, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ctx.sgemm_host(A, B.T.copy(), trans_b=True), A @ B, rtol=1e-5, atol=1e-6)
+
+
+def test_errors_are_reported_not_fatal(ctx):
+    with pytest.raises(capi.GvcError):
+        ctx.forward(np.zeros(3, np.float32), 1.0)     # wrong length is caught on the Python side
+    c = pkg.Context(0)
+    with pytest.raises(capi.GvcError, match="no graph|no model"):
+        c.forward_device(0, 1.0, 0)
+    c.close()
+    with pytest.raises(capi.GvcError, match="out of range"):
+        pkg.Context(99)
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 2 (R-MAT scale 20, 16 M edges), where the oracle would take minutes:
+    size-independent properties instead -- determinism, shard invariance, score range, and
+    agreement of the two arithmetic modes."""
+    g = graphs.rmat_graph(20, 16, seed=42, device="cuda")
+    dev = torch.device("cuda:0")
+    s = 200.0
+    dx = (g.weights.to(torch.float32) / s).contiguous()
+    rp32 = g.row_ptr.to(torch.int32).contiguous()
+    ctx.graph_adopt(rp32, g.col, g.weights, g.nw)
+    a = torch.empty(g.n, device=dev)
+    b = torch.empty(g.n, device=dev)
+    f = torch.empty(g.n, device=dev)
+    torch.cuda.synchronize()
+    ctx.forward_device(dx, s, a, pkg.MODE_EXACT)
+    ctx.forward_device(dx, s, b, pkg.MODE_EXACT)
+    ctx.forward_device(dx, s, f, pkg.MODE_FAST)
+    ctx.sync()
+    assert torch.equal(a, b)                                   # deterministic
+    assert bool(((a >= 0) & (a <= 1)).all()) and bool(torch.isfinite(a).all())
+    rel = ((f - a).abs() / a.abs().clamp_min(1e-30)).max().item()
+    assert rel < FAST_RTOL, rel
+    # a sample of vertices recomputed by the oracle-independent per-layer kernels: same bits
+    # (two different CUDA implementations of the same operation order must agree)

@@ -8,6 +8,7 @@
 // CUDA is unusable every entry point reports an error.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -100,6 +101,9 @@ struct gvc_ctx {
     const uint32_t *row_ptr = nullptr, *col = nullptr, *Wv = nullptr, *NWv = nullptr;   // device views
     DevBuf<uint32_t> own_row_ptr, own_col, own_W, own_NW;
     PinBuf<uint32_t> stage_u32;
+    // schedule (gvc_kernels.cuh): vertices counting-sorted by degree bin + tile classes
+    DevBuf<uint32_t> d_order, d_bins;
+    gvc::TileTable tiles{};
 
     // activations
     DevBuf<float> d_x, d_h1, d_h2, d_scores, d_ping, d_pong;
@@ -248,14 +252,17 @@ template <int STAGE>
 int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int mode) {
     const uint32_t nl = c->n_local();
     if (nl == 0) return 0;
-    const unsigned grid = (nl + kWarpsPerCta * kTileVerts - 1) / (kWarpsPerCta * kTileVerts);
+    const uint32_t n_tiles = c->tiles.first_tile[kNumClasses];
+    const unsigned grid = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t smem = stage_smem_bytes<STAGE>();
     if (mode == GVC_MODE_EXACT) {
         stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, d_in, d_out, c->d_stage_params[STAGE], nl, c->v_begin, scale);
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->tiles, d_in, d_out, c->d_stage_params[STAGE],
+            c->v_begin, scale);
     } else {
         stage_kernel<STAGE, false><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, d_in, d_out, c->d_stage_params[STAGE], nl, c->v_begin, scale);
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->tiles, d_in, d_out, c->d_stage_params[STAGE],
+            c->v_begin, scale);
     }
     GVC_CUDA(cudaGetLastError());
     c->launches++;
@@ -266,6 +273,51 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
         GVC_CUDA(cudaGetLastError());
         c->launches++;
     }
+    return 0;
+}
+
+// Degree-class schedule of the shard's vertices (see gvc_kernels.cuh).  Part of the graph
+// upload: one histogram kernel, a 132-entry scan on the host, one scatter kernel.
+int build_schedule(gvc_ctx *c) {
+    const uint32_t nl = c->n_local();
+    c->tiles = TileTable{};
+    if (nl == 0) return 0;
+    int rc;
+    if ((rc = c->d_order.reserve(nl))) return rc;
+    if ((rc = c->d_bins.reserve(kNumDegBins))) return rc;
+    GVC_CUDA(cudaMemsetAsync(c->d_bins.p, 0, kNumDegBins * sizeof(uint32_t), c->stream));
+    const unsigned grid = std::min<unsigned>(1184, (nl + 255) / 256);
+    degree_hist_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, nl, c->d_bins.p);
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    uint32_t hist[kNumDegBins], start[kNumDegBins];
+    GVC_CUDA(cudaMemcpyAsync(hist, c->d_bins.p, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    uint32_t pos = 0;
+    uint32_t class_pos[kNumClasses + 1];
+    int cls = 0;
+    class_pos[0] = 0;
+    for (int b = kNumDegBins - 1; b >= 0; --b) {          // descending degree
+        while (cls + 1 < kNumClasses && b < degree_bin(class_min_deg(cls))) class_pos[++cls] = pos;
+        start[b] = pos;
+        pos += hist[b];
+    }
+    while (cls + 1 < kNumClasses) class_pos[++cls] = pos;
+    class_pos[kNumClasses] = nl;
+    uint32_t tile = 0;
+    for (int k = 0; k < kNumClasses; ++k) {
+        c->tiles.first_tile[k] = tile;
+        c->tiles.first_pos[k] = class_pos[k];
+        const uint32_t cnt = class_pos[k + 1] - class_pos[k];
+        tile += (cnt + class_verts(k) - 1) / class_verts(k);
+    }
+    c->tiles.first_tile[kNumClasses] = tile;
+    c->tiles.first_pos[kNumClasses] = nl;
+    GVC_CUDA(cudaMemcpyAsync(c->d_bins.p, start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
+    degree_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, nl, c->d_bins.p, c->d_order.p);
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    GVC_CUDA(cudaStreamSynchronize(c->stream));   // `start` lives on this stack frame
     return 0;
 }
 
@@ -356,7 +408,9 @@ int set_graph_views(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_
     c->n_global = n_global; c->v_begin = v_begin; c->v_end = v_end; c->nnz = nnz;
     c->row_ptr = rp; c->col = col; c->Wv = W; c->NWv = NW;
     c->have_graph = true;
-    return ensure_activations(c);
+    int rc;
+    if ((rc = ensure_activations(c))) return rc;
+    return build_schedule(c);
 }
 
 }  // namespace
@@ -403,6 +457,7 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     for (auto &p : c->d_stage_params) if (p) cudaFree(p);
     c->own_row_ptr.release(); c->own_col.release(); c->own_W.release(); c->own_NW.release();
     c->stage_u32.release();
+    c->d_order.release(); c->d_bins.release();
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
     c->d_ping.release(); c->d_pong.release();
     c->pin_x.release(); c->pin_scores.release();

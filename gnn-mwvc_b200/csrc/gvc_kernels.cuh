@@ -35,6 +35,41 @@ constexpr int kTileStride = 36;           // floats per k-row of a tile (32 + 4 
 constexpr int kTileRows = 32;             // widest activation
 constexpr int kTileFloats = kTileRows * kTileStride;
 
+// ---- schedule: which vertices a warp tile holds --------------------------------------
+// Real graphs are skewed (the R-MAT benchmark graph: 40 % isolated vertices, 64 % of the
+// adjacency in vertices of degree > 256, one of degree 64 452) and the reference's sums
+// are sequential per vertex, so the critical path is the largest vertex.  At graph upload
+// the vertices are counting-sorted by degree bin (descending) into `order`, and cut into
+// four classes with different tile shapes:
+//   class 0  deg >= 4096        1 vertex  per tile, warp-cooperative gather
+//   class 1  deg in [1024,4096) 4 vertices per tile, warp-cooperative gather
+//   class 2  deg in [256,1024)  16 vertices per tile, warp-cooperative gather
+//   class 3  deg < 256          32 vertices per tile, 4 lanes per vertex (1 lane for w=1)
+// Heavy tiles come first (longest-processing-time-first); class-3 tiles are dealt
+// alternately from the heavy and the light end so that gather-bound and compute-bound
+// tiles share an SM at any time.  Results do not depend on the schedule.
+constexpr int kNumClasses = 4;
+__host__ __device__ constexpr uint32_t class_min_deg(int c) { return c == 0 ? 4096u : c == 1 ? 1024u : c == 2 ? 256u : 0u; }
+__host__ __device__ constexpr int class_verts(int c) { return c == 0 ? 1 : c == 1 ? 4 : c == 2 ? 16 : 32; }
+constexpr int kNumDegBins = 132;
+
+struct TileTable {
+    uint32_t first_tile[kNumClasses + 1];   // tile index where class c starts; [4] = total tiles
+    uint32_t first_pos[kNumClasses + 1];    // position in `order` where class c starts; [4] = n_local
+};
+
+// degree -> bin, monotone in the degree, 4 bins per octave
+__host__ __device__ __forceinline__ int degree_bin(uint32_t d) {
+    if (d < 4) return (int)d;                  // 0,1,2,3
+#if defined(__CUDA_ARCH__)
+    const int lg = 31 - __clz(d);
+#else
+    int lg = 31;
+    while (!(d >> lg)) --lg;
+#endif
+    return 4 * lg + (int)((d >> (lg - 2)) & 3u) - 4;   // d=4 -> 4, contiguous from there; max 4*31+3-4 = 123
+}
+
 // Packed parameter block of one stage, in floats:
 //   [W_a (Ka x Na)] [b_a (Na)] [W_b (Kb x Nb)] [b_b (Nb)] [W_c (Kc x Nc)] [b_c (Nc)]
 // For the 35-row matrices only rows 0..31 are kept: features 32..34 are +0.0 by
@@ -111,8 +146,9 @@ template <int K, bool EXACT>
 __device__ __forceinline__ void tile_linear_relu_store16(const float *__restrict__ T,
                                                          const float *__restrict__ Wsm,
                                                          const float *__restrict__ bsm, int lane,
-                                                         float *__restrict__ out_rows /* row of tile vertex 0 */,
-                                                         int valid /* vertices of the tile that exist */) {
+                                                         float *__restrict__ out /* global row 0 */,
+                                                         const uint32_t *__restrict__ vid /* smem: global vertex id per slot */,
+                                                         int valid /* slots of the tile that hold a vertex */) {
     const int og = lane >> 3, vg = lane & 7;
     float acc[4][4];
 #pragma unroll
@@ -140,7 +176,7 @@ __device__ __forceinline__ void tile_linear_relu_store16(const float *__restrict
             o.y = relu_ref(__fadd_rn(acc[r][1], b.y));
             o.z = relu_ref(__fadd_rn(acc[r][2], b.z));
             o.w = relu_ref(__fadd_rn(acc[r][3], b.w));
-            *reinterpret_cast<float4 *>(out_rows + (size_t)i * 16 + 4 * og) = o;
+            *reinterpret_cast<float4 *>(out + (size_t)vid[i] * 16 + 4 * og) = o;
         }
     }
 }
@@ -152,23 +188,26 @@ __device__ __forceinline__ float sigmoid_ref(float v) {
     else return 1.0f / (1.0f + expf(-v));
 }
 
-// ---- phase A, width 16: 4 lanes per vertex, 8 vertices per pass ---------------
+// ---- phase A, width 16, class 3: 4 lanes per vertex, 8 vertices per pass ----------------
+// vid[i] receives the GLOBAL id of the vertex in slot i.
 template <bool EXACT>
-__device__ __forceinline__ void gather16_tile(float *__restrict__ T, const uint32_t *__restrict__ row_ptr,
+__device__ __forceinline__ void gather16_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
+                                              const uint32_t *__restrict__ order, uint32_t pos0, int count,
+                                              const uint32_t *__restrict__ row_ptr,
                                               const uint32_t *__restrict__ col,
                                               const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
-                                              const float4 *__restrict__ in4, uint32_t tile_base,
-                                              uint32_t n_local, uint32_t v_begin, float scale, int lane) {
+                                              const float4 *__restrict__ in4, uint32_t v_begin, float scale,
+                                              int lane) {
     const int sv = lane >> 2, q = lane & 3;
 #pragma unroll 1
     for (int p = 0; p < 4; ++p) {
         const int i = p * 8 + sv;
-        const uint32_t ul = tile_base + i;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ul < n_local) {
-            uint32_t e = row_ptr[ul];
-            const uint32_t end = row_ptr[ul + 1];
+        if (i < count) {
+            const uint32_t ul = __ldg(order + pos0 + i);
+            uint32_t e = __ldg(row_ptr + ul);
+            const uint32_t end = __ldg(row_ptr + ul + 1);
             const uint32_t deg = end - e;
             for (; e + 4 <= end; e += 4) {
                 const uint32_t v0 = __ldg(col + e), v1 = __ldg(col + e + 1), v2 = __ldg(col + e + 2),
@@ -192,6 +231,7 @@ __device__ __forceinline__ void gather16_tile(float *__restrict__ T, const uint3
                 self.y = __uint2float_rn(deg);
                 self.z = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
                 self.w = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
+                vid[i] = v_begin + ul;
             }
         }
         float *t = T + (4 * q) * kTileStride + i;
@@ -202,17 +242,119 @@ __device__ __forceinline__ void gather16_tile(float *__restrict__ T, const uint3
     __syncwarp();
 }
 
-// ---- phase A, width 1: one lane per vertex -------------------------------------
-__device__ __forceinline__ void gather1_tile(float *__restrict__ T, const uint32_t *__restrict__ row_ptr,
+// ---- phase A, width 16, classes 0-2: the whole warp gathers ONE vertex -------------------
+// 64 neighbour rows per batch: every lane fetches 8 x 16 B (8 rows per load wave, fully
+// coalesced per row), the next batch is in flight while the current one is summed.  The
+// sum itself is the reference's sequential chain: rows are parked in the warp's tile
+// buffer and lane c (< 16) adds column c in adjacency order, 4 cycles per neighbour.
+// Returns acc[c] in lanes 0..15.
+__device__ __forceinline__ void coop_load_batch16(float4 (&r)[8], const uint32_t *__restrict__ col,
+                                                  const float4 *__restrict__ in4, uint32_t e0, uint32_t end,
+                                                  int lane) {
+    const int sv = lane >> 2, q = lane & 3;
+    const uint32_t id0 = (e0 + lane < end) ? __ldg(col + e0 + lane) : 0u;
+    const uint32_t id1 = (e0 + 32 + lane < end) ? __ldg(col + e0 + 32 + lane) : 0u;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int j = 8 * w + sv;
+        const uint32_t id = __shfl_sync(0xffffffffu, (w < 4) ? id0 : id1, j & 31);
+        r[w] = (e0 + j < end) ? ldg_row4(in4 + (size_t)id * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+__device__ __forceinline__ float coop_gather16(float *__restrict__ S /* >= 1024 floats */,
+                                               const uint32_t *__restrict__ col,
+                                               const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
+                                               int lane) {
+    const int sv = lane >> 2, q = lane & 3;
+    const int c = lane & 15;
+    float acc = 0.0f;
+    if (beg >= end) return acc;
+    float4 cur[8], nxt[8];
+    coop_load_batch16(cur, col, in4, beg, end, lane);
+#pragma unroll 1
+    for (uint32_t e = beg; e < end; e += 64) {
+        const bool more = e + 64 < end;            // warp-uniform
+        if (more) coop_load_batch16(nxt, col, in4, e + 64, end, lane);
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+            *reinterpret_cast<float4 *>(S + (8 * w + sv) * 16 + 4 * q) = cur[w];
+        __syncwarp();
+        const int cnt = (int)min(64u, end - e);
+        const float *s = S + c;
+        int j = 0;
+        for (; j + 16 <= cnt; j += 16) {
+            float v[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) v[t] = s[(j + t) * 16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc = __fadd_rn(acc, v[t]);
+        }
+        for (; j < cnt; ++j) acc = __fadd_rn(acc, s[j * 16]);
+        __syncwarp();
+        if (more) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) cur[w] = nxt[w];
+        }
+    }
+    return acc;
+}
+
+// Classes 0-2 tile: `count` vertices, one after the other, each gathered by the whole warp.
+// The gather uses the tile buffer as staging, so the feature columns are collected in
+// registers first (lane c < 16 keeps agg[c] of vertex i in slot register i ... too many
+// registers for 16 vertices) -- instead features go to the upper half of the buffer:
+// staging = floats [0, 1024), feature columns are written after the gather of each vertex
+// into a side strip F (kWarpFeat floats) and copied into the tile at the end.
+template <bool EXACT>
+__device__ __forceinline__ void gather16_coop_tile(float *__restrict__ T, float *__restrict__ F,
+                                                   uint32_t *__restrict__ vid,
+                                                   const uint32_t *__restrict__ order, uint32_t pos0, int count,
+                                                   const uint32_t *__restrict__ row_ptr,
+                                                   const uint32_t *__restrict__ col,
+                                                   const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+                                                   const float *__restrict__ in, uint32_t v_begin, float scale,
+                                                   int lane) {
+    const float4 *in4 = reinterpret_cast<const float4 *>(in);
+#pragma unroll 1
+    for (int i = 0; i < count; ++i) {
+        const uint32_t ul = __ldg(order + pos0 + i);
+        const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+        const float acc = coop_gather16(T, col, in4, beg, end, lane);
+        // feature vector of vertex i -> F[i][0..32): lanes 0-15 agg, lanes 16-31 self (+ quirk)
+        float f;
+        if (lane < 16) {
+            f = acc;
+        } else {
+            const int c = lane - 16;
+            f = __ldg(in + (size_t)(v_begin + ul) * 16 + c);
+            if (c == 1) f = __uint2float_rn(end - beg);
+            if (c == 2) f = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
+            if (c == 3) f = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
+        }
+        F[i * 32 + lane] = f;
+        if (lane == 0) vid[i] = v_begin + ul;
+    }
+    __syncwarp();
+    // F[i][k] -> T[k][i]; unused slots are zero-filled (their results are never stored)
+    for (int i = 0; i < kTileVerts; ++i)
+        T[lane * kTileStride + i] = (i < count) ? F[i * 32 + lane] : 0.0f;
+    __syncwarp();
+}
+
+// ---- phase A, width 1, class 3: one lane per vertex -------------------------------------------
+__device__ __forceinline__ void gather1_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
+                                             const uint32_t *__restrict__ order, uint32_t pos0, int count,
+                                             const uint32_t *__restrict__ row_ptr,
                                              const uint32_t *__restrict__ col,
                                              const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
-                                             const float *__restrict__ x, uint32_t tile_base,
-                                             uint32_t n_local, uint32_t v_begin, float scale, int lane) {
-    const uint32_t ul = tile_base + lane;
+                                             const float *__restrict__ x, uint32_t v_begin, float scale,
+                                             int lane) {
     float agg = 0.0f, xs = 0.0f, fd = 0.0f, fw = 0.0f, fnw = 0.0f;
-    if (ul < n_local) {
-        uint32_t e = row_ptr[ul];
-        const uint32_t end = row_ptr[ul + 1];
+    if (lane < count) {
+        const uint32_t ul = __ldg(order + pos0 + lane);
+        uint32_t e = __ldg(row_ptr + ul);
+        const uint32_t end = __ldg(row_ptr + ul + 1);
         fd = __uint2float_rn(end - e);
         for (; e + 4 <= end; e += 4) {
             const uint32_t v0 = __ldg(col + e), v1 = __ldg(col + e + 1), v2 = __ldg(col + e + 2),
@@ -224,6 +366,7 @@ __device__ __forceinline__ void gather1_tile(float *__restrict__ T, const uint32
         xs = __ldg(x + v_begin + ul);
         fw = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
         fnw = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
+        vid[lane] = v_begin + ul;
     }
     T[0 * kTileStride + lane] = agg;    // [agg | x | D | W/s | NW/s], :33-40 with w = 1
     T[1 * kTileStride + lane] = xs;
@@ -233,46 +376,121 @@ __device__ __forceinline__ void gather1_tile(float *__restrict__ T, const uint32
     __syncwarp();
 }
 
+// ---- phase A, width 1, classes 0-2: the whole warp gathers ONE vertex ---------------------------
+// 32 neighbours per load (coalesced ids, gathered x), two loads ahead; the sequential sum
+// walks the 32 values with shuffles (every lane keeps the same running sum).
+__device__ __forceinline__ float coop_gather1(const uint32_t *__restrict__ col, const float *__restrict__ x,
+                                              uint32_t beg, uint32_t end, int lane) {
+    float acc = 0.0f;
+    if (beg >= end) return acc;
+    auto load = [&](uint32_t e0) { return (e0 + lane < end) ? __ldg(x + __ldg(col + e0 + lane)) : 0.0f; };
+    float v0 = load(beg), v1 = load(beg + 32), v2 = load(beg + 64);
+#pragma unroll 1
+    for (uint32_t e = beg; e < end; e += 32) {
+        const float v3 = load(e + 96);
+        const int cnt = (int)min(32u, end - e);
+        if (cnt == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v0, j));
+        } else {
+            for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v0, j));
+        }
+        v0 = v1; v1 = v2; v2 = v3;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void gather1_coop_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
+                                                  const uint32_t *__restrict__ order, uint32_t pos0, int count,
+                                                  const uint32_t *__restrict__ row_ptr,
+                                                  const uint32_t *__restrict__ col,
+                                                  const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+                                                  const float *__restrict__ x, uint32_t v_begin, float scale,
+                                                  int lane) {
+    float f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};    // lane i keeps the features of slot i
+#pragma unroll 1
+    for (int i = 0; i < count; ++i) {
+        const uint32_t ul = __ldg(order + pos0 + i);
+        const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+        const float acc = coop_gather1(col, x, beg, end, lane);
+        if (lane == i) {
+            f[0] = acc;
+            f[1] = __ldg(x + v_begin + ul);
+            f[2] = __uint2float_rn(end - beg);
+            f[3] = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
+            f[4] = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
+            vid[i] = v_begin + ul;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) T[k * kTileStride + lane] = f[k];
+    __syncwarp();
+}
+
 // ---- the fused stage kernel ------------------------------------------------------
 // STAGE 0: in = x [n_global], out = h rows [n_global x 16]
 // STAGE 1: in = h [n_global x 16], out = h rows [n_global x 16]
 // STAGE 2: in = h [n_global x 16], out = scores [n_local]
+constexpr int kWarpFeat = 16 * 32;                                   // side strip F of the cooperative tiles
+constexpr int kWarpSmemFloats = kTileFloats + kWarpFeat + 32;        // tile + F + vid
+
 template <int STAGE, bool EXACT>
 __global__ void __launch_bounds__(kCtaThreads, 3)
 stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
              const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+             const uint32_t *__restrict__ order, const TileTable tt,
              const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ params,
-             uint32_t n_local, uint32_t v_begin, float scale) {
+             uint32_t v_begin, float scale) {
     constexpr StageDims D = stage_dims(STAGE);
     extern __shared__ __align__(16) float smem[];
     float *P = smem;                                             // packed parameters
     constexpr int kParamFloats = (D.floats() + 3) / 4 * 4;
-    float *tiles = smem + kParamFloats;
+    float *warp_mem = smem + kParamFloats;
 
     for (int i = threadIdx.x; i < D.floats(); i += kCtaThreads) P[i] = __ldg(params + i);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tile_base = (blockIdx.x * kWarpsPerCta + warp) * kTileVerts;
-    if (tile_base >= n_local) return;
-    float *T = tiles + warp * kTileFloats;
+    const uint32_t t = blockIdx.x * kWarpsPerCta + warp;
+    if (t >= tt.first_tile[kNumClasses]) return;
+    float *T = warp_mem + warp * kWarpSmemFloats;
+    float *F = T + kTileFloats;
+    uint32_t *vid = reinterpret_cast<uint32_t *>(F + kWarpFeat);
+
+    // tile -> class, position range
+    int cls = 0;
+#pragma unroll
+    for (int c = 1; c < kNumClasses; ++c) cls += (t >= tt.first_tile[c]) ? 1 : 0;
+    uint32_t lt = t - tt.first_tile[cls];
+    const int vpt = class_verts(cls);
+    if (cls == kNumClasses - 1) {     // deal class-3 tiles alternately from the heavy and the light end
+        const uint32_t nt = tt.first_tile[kNumClasses] - tt.first_tile[cls];
+        lt = (lt & 1u) ? nt - 1 - (lt >> 1) : (lt >> 1);
+    }
+    const uint32_t pos0 = tt.first_pos[cls] + lt * (uint32_t)vpt;
+    const int count = (int)min((uint32_t)vpt, tt.first_pos[cls + 1] - pos0);
 
     const float *Wa = P, *ba = Wa + D.Ka * D.Na;
     const float *Wb = ba + D.Na, *bb = Wb + D.Kb * D.Nb;
     const float *Wc = bb + D.Nb, *bc = Wc + D.Kc * D.Nc;
 
-    if constexpr (STAGE == 0)
-        gather1_tile(T, row_ptr, col, Wv, NWv, in, tile_base, n_local, v_begin, scale, lane);
-    else
-        gather16_tile<EXACT>(T, row_ptr, col, Wv, NWv, reinterpret_cast<const float4 *>(in), tile_base,
-                             n_local, v_begin, scale, lane);
+    if constexpr (STAGE == 0) {
+        if (cls == kNumClasses - 1)
+            gather1_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);
+        else
+            gather1_coop_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);
+    } else {
+        if (cls == kNumClasses - 1)
+            gather16_tile<EXACT>(T, vid, order, pos0, count, row_ptr, col, Wv, NWv,
+                                 reinterpret_cast<const float4 *>(in), v_begin, scale, lane);
+        else
+            gather16_coop_tile<EXACT>(T, F, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);
+    }
 
-    const int valid = (int)min((uint32_t)kTileVerts, n_local - tile_base);
     if constexpr (STAGE < 2) {
         tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane);
         tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane);
-        tile_linear_relu_store16<D.Kc, EXACT>(T, Wc, bc, lane,
-                                              out + (size_t)(v_begin + tile_base) * 16, valid);
+        tile_linear_relu_store16<D.Kc, EXACT>(T, Wc, bc, lane, out, vid, count);
     } else {
         tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane);
         tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane);
@@ -285,14 +503,37 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
             od = mac<EXACT>(T[(k + 1) * kTileStride + lane], Wc[k + 1], od);
         }
         const float s = __fadd_rn(__fadd_rn(ev, od), bc[0]);
-        if (lane < valid) out[tile_base + lane] = sigmoid_ref<EXACT>(s);
+        if (lane < count) out[vid[lane] - v_begin] = sigmoid_ref<EXACT>(s);
     }
 }
 
 template <int STAGE>
 constexpr size_t stage_smem_bytes() {
     constexpr StageDims D = stage_dims(STAGE);
-    return ((D.floats() + 3) / 4 * 4 + kWarpsPerCta * kTileFloats) * sizeof(float);
+    return ((D.floats() + 3) / 4 * 4 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
+}
+
+// ---- schedule construction (graph upload time) -------------------------------------------
+// counting sort of the local vertices by degree bin: histogram, (host) scan, scatter
+__global__ void degree_hist_kernel(const uint32_t *__restrict__ row_ptr, uint32_t n_local,
+                                   uint32_t *__restrict__ hist /* kNumDegBins, zeroed */) {
+    __shared__ uint32_t sh[kNumDegBins];
+    for (int i = threadIdx.x; i < kNumDegBins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_local; u += gridDim.x * blockDim.x)
+        atomicAdd(&sh[degree_bin(row_ptr[u + 1] - row_ptr[u])], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kNumDegBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+__global__ void degree_scatter_kernel(const uint32_t *__restrict__ row_ptr, uint32_t n_local,
+                                      uint32_t *__restrict__ cursor /* kNumDegBins: start of each bin */,
+                                      uint32_t *__restrict__ order) {
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_local; u += gridDim.x * blockDim.x) {
+        const uint32_t pos = atomicAdd(&cursor[degree_bin(row_ptr[u + 1] - row_ptr[u])], 1u);
+        order[pos] = u;
+    }
 }
 
 // ---- exact-mode tail: the last vertex of an odd-sized graph ---------------------

@@ -209,22 +209,26 @@ __device__ __forceinline__ void gather16_tile(float *__restrict__ T, uint32_t *_
             uint32_t e = __ldg(row_ptr + ul);
             const uint32_t end = __ldg(row_ptr + ul + 1);
             const uint32_t deg = end - e;
-            for (; e + 4 <= end; e += 4) {
-                const uint32_t v0 = __ldg(col + e), v1 = __ldg(col + e + 1), v2 = __ldg(col + e + 2),
-                               v3 = __ldg(col + e + 3);
-                const float4 r0 = ldg_row4(in4 + (size_t)v0 * 4 + q);
-                const float4 r1 = ldg_row4(in4 + (size_t)v1 * 4 + q);
-                const float4 r2 = ldg_row4(in4 + (size_t)v2 * 4 + q);
-                const float4 r3 = ldg_row4(in4 + (size_t)v3 * 4 + q);
-                acc.x = __fadd_rn(acc.x, r0.x); acc.y = __fadd_rn(acc.y, r0.y); acc.z = __fadd_rn(acc.z, r0.z); acc.w = __fadd_rn(acc.w, r0.w);
-                acc.x = __fadd_rn(acc.x, r1.x); acc.y = __fadd_rn(acc.y, r1.y); acc.z = __fadd_rn(acc.z, r1.z); acc.w = __fadd_rn(acc.w, r1.w);
-                acc.x = __fadd_rn(acc.x, r2.x); acc.y = __fadd_rn(acc.y, r2.y); acc.z = __fadd_rn(acc.z, r2.z); acc.w = __fadd_rn(acc.w, r2.w);
-                acc.x = __fadd_rn(acc.x, r3.x); acc.y = __fadd_rn(acc.y, r3.y); acc.z = __fadd_rn(acc.z, r3.z); acc.w = __fadd_rn(acc.w, r3.w);
-            }
-            for (; e < end; ++e) {
-                const uint32_t v = __ldg(col + e);
-                const float4 r = ldg_row4(in4 + (size_t)v * 4 + q);
-                acc.x = __fadd_rn(acc.x, r.x); acc.y = __fadd_rn(acc.y, r.y); acc.z = __fadd_rn(acc.z, r.z); acc.w = __fadd_rn(acc.w, r.w);
+            // ids are fetched one iteration ahead of the rows they address, so the two
+            // dependent load latencies (col -> row) overlap instead of adding up
+            uint32_t id[8], nid[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) id[t] = (e + t < end) ? __ldg(col + e + t) : 0u;
+            for (; e < end; e += 8) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) nid[t] = (e + 8 + t < end) ? __ldg(col + e + 8 + t) : 0u;
+                float4 r[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (e + t < end) r[t] = ldg_row4(in4 + (size_t)id[t] * 4 + q);
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (e + t < end) {
+                        acc.x = __fadd_rn(acc.x, r[t].x); acc.y = __fadd_rn(acc.y, r[t].y);
+                        acc.z = __fadd_rn(acc.z, r[t].z); acc.w = __fadd_rn(acc.w, r[t].w);
+                    }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) id[t] = nid[t];
             }
             self = ldg_row4(in4 + (size_t)(v_begin + ul) * 4 + q);                     // :37
             if (q == 0) {   // the quirk: D, W/s, NW/s overwrite self features 1..3 (:38-40)
@@ -248,20 +252,31 @@ __device__ __forceinline__ void gather16_tile(float *__restrict__ T, uint32_t *_
 // sum itself is the reference's sequential chain: rows are parked in the warp's tile
 // buffer and lane c (< 16) adds column c in adjacency order, 4 cycles per neighbour.
 // Returns acc[c] in lanes 0..15.
-__device__ __forceinline__ void coop_load_batch16(float4 (&r)[8], const uint32_t *__restrict__ col,
-                                                  const float4 *__restrict__ in4, uint32_t e0, uint32_t end,
+struct BatchIds { uint32_t lo, hi; };   // lane l holds neighbour ids e0+l and e0+32+l
+
+__device__ __forceinline__ BatchIds coop_load_ids(const uint32_t *__restrict__ col, uint32_t e0, uint32_t end,
                                                   int lane) {
+    BatchIds b;
+    b.lo = (e0 + lane < end) ? __ldg(col + e0 + lane) : 0u;
+    b.hi = (e0 + 32 + lane < end) ? __ldg(col + e0 + 32 + lane) : 0u;
+    return b;
+}
+
+__device__ __forceinline__ void coop_load_rows16(float4 (&r)[8], const BatchIds ids,
+                                                 const float4 *__restrict__ in4, uint32_t e0, uint32_t end,
+                                                 int lane) {
     const int sv = lane >> 2, q = lane & 3;
-    const uint32_t id0 = (e0 + lane < end) ? __ldg(col + e0 + lane) : 0u;
-    const uint32_t id1 = (e0 + 32 + lane < end) ? __ldg(col + e0 + 32 + lane) : 0u;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
         const int j = 8 * w + sv;
-        const uint32_t id = __shfl_sync(0xffffffffu, (w < 4) ? id0 : id1, j & 31);
+        const uint32_t id = __shfl_sync(0xffffffffu, (w < 4) ? ids.lo : ids.hi, j & 31);
         r[w] = (e0 + j < end) ? ldg_row4(in4 + (size_t)id * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
+// Software pipeline per 64-neighbour batch b: ids of b+2 and rows of b+1 are in flight
+// while batch b is summed (the warp issues in order, so a load must never be consumed in
+// the iteration that issued it).
 __device__ __forceinline__ float coop_gather16(float *__restrict__ S /* >= 1024 floats */,
                                                const uint32_t *__restrict__ col,
                                                const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
@@ -271,26 +286,40 @@ __device__ __forceinline__ float coop_gather16(float *__restrict__ S /* >= 1024 
     float acc = 0.0f;
     if (beg >= end) return acc;
     float4 cur[8], nxt[8];
-    coop_load_batch16(cur, col, in4, beg, end, lane);
+    BatchIds ids0 = coop_load_ids(col, beg, end, lane);
+    BatchIds ids1 = coop_load_ids(col, beg + 64, end, lane);
+    coop_load_rows16(cur, ids0, in4, beg, end, lane);
 #pragma unroll 1
     for (uint32_t e = beg; e < end; e += 64) {
         const bool more = e + 64 < end;            // warp-uniform
-        if (more) coop_load_batch16(nxt, col, in4, e + 64, end, lane);
+        if (more) coop_load_rows16(nxt, ids1, in4, e + 64, end, lane);
+        ids1 = coop_load_ids(col, e + 128, end, lane);
 #pragma unroll
         for (int w = 0; w < 8; ++w)
             *reinterpret_cast<float4 *>(S + (8 * w + sv) * 16 + 4 * q) = cur[w];
         __syncwarp();
         const int cnt = (int)min(64u, end - e);
         const float *s = S + c;
-        int j = 0;
-        for (; j + 16 <= cnt; j += 16) {
-            float v[16];
+        if (cnt == 64) {
+            float va[16], vb[16];
 #pragma unroll
-            for (int t = 0; t < 16; ++t) v[t] = s[(j + t) * 16];
+            for (int t = 0; t < 16; ++t) va[t] = s[t * 16];
 #pragma unroll
-            for (int t = 0; t < 16; ++t) acc = __fadd_rn(acc, v[t]);
+            for (int g = 0; g < 4; g += 2) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) vb[t] = s[((g + 1) * 16 + t) * 16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) acc = __fadd_rn(acc, va[t]);
+                if (g + 2 < 4) {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) va[t] = s[((g + 2) * 16 + t) * 16];
+                }
+#pragma unroll
+                for (int t = 0; t < 16; ++t) acc = __fadd_rn(acc, vb[t]);
+            }
+        } else {
+            for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, s[j * 16]);
         }
-        for (; j < cnt; ++j) acc = __fadd_rn(acc, s[j * 16]);
         __syncwarp();
         if (more) {
 #pragma unroll
@@ -356,13 +385,21 @@ __device__ __forceinline__ void gather1_tile(float *__restrict__ T, uint32_t *__
         uint32_t e = __ldg(row_ptr + ul);
         const uint32_t end = __ldg(row_ptr + ul + 1);
         fd = __uint2float_rn(end - e);
-        for (; e + 4 <= end; e += 4) {
-            const uint32_t v0 = __ldg(col + e), v1 = __ldg(col + e + 1), v2 = __ldg(col + e + 2),
-                           v3 = __ldg(col + e + 3);
-            const float a0 = __ldg(x + v0), a1 = __ldg(x + v1), a2 = __ldg(x + v2), a3 = __ldg(x + v3);
-            agg = __fadd_rn(agg, a0); agg = __fadd_rn(agg, a1); agg = __fadd_rn(agg, a2); agg = __fadd_rn(agg, a3);
+        uint32_t id[8], nid[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) id[t] = (e + t < end) ? __ldg(col + e + t) : 0u;
+        for (; e < end; e += 8) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) nid[t] = (e + 8 + t < end) ? __ldg(col + e + 8 + t) : 0u;
+            float a[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) a[t] = (e + t < end) ? __ldg(x + id[t]) : 0.0f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (e + t < end) agg = __fadd_rn(agg, a[t]);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) id[t] = nid[t];
         }
-        for (; e < end; ++e) agg = __fadd_rn(agg, __ldg(x + __ldg(col + e)));
         xs = __ldg(x + v_begin + ul);
         fw = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
         fnw = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
@@ -383,11 +420,16 @@ __device__ __forceinline__ float coop_gather1(const uint32_t *__restrict__ col, 
                                               uint32_t beg, uint32_t end, int lane) {
     float acc = 0.0f;
     if (beg >= end) return acc;
-    auto load = [&](uint32_t e0) { return (e0 + lane < end) ? __ldg(x + __ldg(col + e0 + lane)) : 0.0f; };
-    float v0 = load(beg), v1 = load(beg + 32), v2 = load(beg + 64);
+    auto ld_id = [&](uint32_t e0) { return (e0 + lane < end) ? __ldg(col + e0 + lane) : 0u; };
+    auto ld_x = [&](uint32_t id, uint32_t e0) { return (e0 + lane < end) ? __ldg(x + id) : 0.0f; };
+    // pipeline per 32-neighbour batch b: ids of b+3..b+6 and values of b+1..b+2 in flight
+    uint32_t i0 = ld_id(beg), i1 = ld_id(beg + 32), i2 = ld_id(beg + 64), i3 = ld_id(beg + 96),
+             i4 = ld_id(beg + 128), i5 = ld_id(beg + 160);
+    float v0 = ld_x(i0, beg), v1 = ld_x(i1, beg + 32);
 #pragma unroll 1
     for (uint32_t e = beg; e < end; e += 32) {
-        const float v3 = load(e + 96);
+        const float v2 = ld_x(i2, e + 64);
+        const uint32_t i6 = ld_id(e + 192);
         const int cnt = (int)min(32u, end - e);
         if (cnt == 32) {
 #pragma unroll
@@ -395,7 +437,8 @@ __device__ __forceinline__ float coop_gather1(const uint32_t *__restrict__ col, 
         } else {
             for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v0, j));
         }
-        v0 = v1; v1 = v2; v2 = v3;
+        v0 = v1; v1 = v2;
+        i2 = i3; i3 = i4; i4 = i5; i5 = i6;
     }
     return acc;
 }

@@ -39,7 +39,8 @@ def build_libgvc(force: bool = False, verbose: bool = False) -> Path:
     srcs = [PKG / "csrc" / "gvc_api.cu", PKG / "csrc" / "gvc_kernels.cuh", PKG / "csrc" / "gvc_expf.h",
             ROOT / "include" / "gvc.h"]
     if force or _stale(out, srcs):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(out), str(srcs[0])]
+        extra = os.environ.get("GVC_NVCC_EXTRA", "").split()     # e.g. -DGVC_CTAS_PER_SM=2 for experiments
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", str(out), str(srcs[0])]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

@@ -102,8 +102,10 @@ struct gvc_ctx {
     DevBuf<uint32_t> own_row_ptr, own_col, own_W, own_NW;
     PinBuf<uint32_t> stage_u32;
     // schedule (gvc_kernels.cuh): vertices counting-sorted by degree bin + tile classes
-    DevBuf<uint32_t> d_order, d_bins;
-    gvc::TileTable tiles{};
+    DevBuf<uint32_t> d_order, d_bins, d_sync;
+    DevBuf<float> d_feat;
+    gvc::Schedule sched{};
+    int num_sms = 148;
 
     // activations
     DevBuf<float> d_x, d_h1, d_h2, d_scores, d_ping, d_pong;
@@ -252,17 +254,21 @@ template <int STAGE>
 int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int mode) {
     const uint32_t nl = c->n_local();
     if (nl == 0) return 0;
-    const uint32_t n_tiles = c->tiles.first_tile[kNumClasses];
-    const unsigned grid = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+    const Schedule &sc = c->sched;
+    const uint32_t n_tasks = sc.n_coop + sc.n_tiles + sc.n_feat_tiles;
+    const unsigned want = std::max<unsigned>(sc.n_ring, (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
+    const unsigned grid = std::max(1u, std::min<unsigned>(kCtasPerSm * c->num_sms, want));
     const size_t smem = stage_smem_bytes<STAGE>();
+    // task counter + per-feature-tile completion counters start at zero
+    GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (1 + (size_t)sc.n_feat_tiles) * sizeof(uint32_t), c->stream));
     if (mode == GVC_MODE_EXACT) {
         stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->tiles, d_in, d_out, c->d_stage_params[STAGE],
-            c->v_begin, scale);
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, sc, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->d_stage_params[STAGE], c->v_begin, scale);
     } else {
         stage_kernel<STAGE, false><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->tiles, d_in, d_out, c->d_stage_params[STAGE],
-            c->v_begin, scale);
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, sc, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->d_stage_params[STAGE], c->v_begin, scale);
     }
     GVC_CUDA(cudaGetLastError());
     c->launches++;
@@ -276,11 +282,11 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     return 0;
 }
 
-// Degree-class schedule of the shard's vertices (see gvc_kernels.cuh).  Part of the graph
-// upload: one histogram kernel, a 132-entry scan on the host, one scatter kernel.
+// Degree schedule of the shard's vertices (see gvc_kernels.cuh).  Part of the graph upload:
+// one histogram kernel, a 132-entry scan on the host, one scatter kernel.
 int build_schedule(gvc_ctx *c) {
     const uint32_t nl = c->n_local();
-    c->tiles = TileTable{};
+    c->sched = Schedule{};
     if (nl == 0) return 0;
     int rc;
     if ((rc = c->d_order.reserve(nl))) return rc;
@@ -293,26 +299,21 @@ int build_schedule(gvc_ctx *c) {
     uint32_t hist[kNumDegBins], start[kNumDegBins];
     GVC_CUDA(cudaMemcpyAsync(hist, c->d_bins.p, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));
-    uint32_t pos = 0;
-    uint32_t class_pos[kNumClasses + 1];
-    int cls = 0;
-    class_pos[0] = 0;
+    uint32_t pos = 0, n_ring = 0, n_pre = 0;
     for (int b = kNumDegBins - 1; b >= 0; --b) {          // descending degree
-        while (cls + 1 < kNumClasses && b < degree_bin(class_min_deg(cls))) class_pos[++cls] = pos;
+        if (b == degree_bin(kRingMinDeg) - 1) n_ring = pos;
+        if (b == degree_bin(kCoopMinDeg) - 1) n_pre = pos;
         start[b] = pos;
         pos += hist[b];
     }
-    while (cls + 1 < kNumClasses) class_pos[++cls] = pos;
-    class_pos[kNumClasses] = nl;
-    uint32_t tile = 0;
-    for (int k = 0; k < kNumClasses; ++k) {
-        c->tiles.first_tile[k] = tile;
-        c->tiles.first_pos[k] = class_pos[k];
-        const uint32_t cnt = class_pos[k + 1] - class_pos[k];
-        tile += (cnt + class_verts(k) - 1) / class_verts(k);
-    }
-    c->tiles.first_tile[kNumClasses] = tile;
-    c->tiles.first_pos[kNumClasses] = nl;
+    Schedule &sc = c->sched;
+    sc.n_local = nl;
+    sc.n_ring = n_ring;
+    sc.n_coop = n_pre - n_ring;
+    sc.n_tiles = (nl - n_pre + kTileVerts - 1) / kTileVerts;
+    sc.n_feat_tiles = (n_pre + kTileVerts - 1) / kTileVerts;
+    if ((rc = c->d_feat.reserve((size_t)n_pre * 32))) return rc;
+    if ((rc = c->d_sync.reserve(1 + (size_t)sc.n_feat_tiles))) return rc;
     GVC_CUDA(cudaMemcpyAsync(c->d_bins.p, start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
     degree_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, nl, c->d_bins.p, c->d_order.p);
     GVC_CUDA(cudaGetLastError());
@@ -436,6 +437,7 @@ int gvc_ctx_create(gvc_ctx **out, int device) {
     gvc_ctx *c = new (std::nothrow) gvc_ctx();
     if (!c) return fail(GVC_ERR_ALLOC, "out of host memory");
     c->device = device;
+    c->num_sms = prop.multiProcessorCount;
     GVC_CUDA(cudaSetDevice(device));
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(1000 + (int)e, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
@@ -457,7 +459,7 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     for (auto &p : c->d_stage_params) if (p) cudaFree(p);
     c->own_row_ptr.release(); c->own_col.release(); c->own_W.release(); c->own_NW.release();
     c->stage_u32.release();
-    c->d_order.release(); c->d_bins.release();
+    c->d_order.release(); c->d_bins.release(); c->d_sync.release(); c->d_feat.release();
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
     c->d_ping.release(); c->d_pong.release();
     c->pin_x.release(); c->pin_scores.release();

@@ -3,23 +3,40 @@
 //
 // One "stage" = one graph layer (src/gnn_inference.cpp:27-42) fused with the
 // dense layers, bias adds and activations that follow it (:20-25, :44-52) up to
-// the next graph layer.  A warp owns a tile of 32 vertices from gather to
-// store; nothing but the 16-float stage output per vertex goes back to HBM.
+// the next graph layer.  Nothing but the 16-float stage output per vertex (or the
+// score) goes back to HBM.
 //
-//   phase A  gather-aggregate: neighbour rows are summed in adjacency order
-//            (the order the reference adds them, :33-36) with 128-bit loads,
-//            4 lanes per 64-byte row; the concatenated feature vector of
-//            :37-40 -- including its column quirk, SURVEY.md A.2 -- is written
-//            k-major into the warp's shared-memory tile, never to HBM.
-//   phase B  dense chain on CUDA cores: each lane keeps a 4-vertex x 8-output
-//            (or 4 x 4) block of accumulators in registers, reads activations
-//            and weights from shared memory with 128-bit loads, applies bias
-//            and ReLU in registers and writes the next activation tile in place.
-//   phase C  store: 16 floats per vertex (stages 0/1) or the sigmoid score.
+//   gather   neighbour rows are summed in adjacency order -- the order the
+//            reference adds them (:33-36) -- with 128-bit loads, 4 lanes per
+//            64-byte row; the concatenated feature vector of :37-40 (including
+//            its column quirk) is built on chip.
+//   dense    a warp owns a tile of 32 vertices: each lane keeps a 4-vertex x
+//            8-output (or 4 x 4) block of accumulators in registers, reads
+//            activations and weights from shared memory with 128-bit loads,
+//            applies bias and ReLU in registers and rewrites the tile in place.
+//   store    16 floats per vertex (stages 0/1) or the sigmoid score.
 //
 // EXACT=true keeps the reference's fp32 operation order (one accumulator per
-// output, k ascending, product and sum rounded separately, see
-// oracle/gnn_oracle.c) -> bit-identical scores.  EXACT=false contracts to FFMA.
+// output, k ascending, product and sum rounded separately, sequential
+// neighbour sums; see oracle/gnn_oracle.c) -> bit-identical scores.
+// EXACT=false contracts to FFMA and uses the device expf.
+//
+// Scheduling.  Real graphs are skewed (the R-MAT benchmark graph: 40 % isolated
+// vertices, 80 % of the adjacency in vertices of degree >= 64, one vertex of
+// degree 64 452) and the sums are sequential per vertex, so work is organised by
+// degree (the vertices are counting-sorted by degree bin at graph upload):
+//   ring    deg >= 2048   all 8 warps of a CTA serve ONE vertex: each warp
+//                         fetches every 8th 64-row batch, the running sum is
+//                         handed from warp to warp through named barriers, so
+//                         512 rows are in flight for a single sequential chain
+//   coop    64 <= deg     one warp per vertex, 64 rows in flight, next batch's
+//           < 2048        rows and the batch after's ids prefetched
+//   tile    deg < 64      32 vertices per warp, 4 lanes per vertex (1 for w=1)
+// ring and coop tasks only produce the 32-float feature vector (side buffer,
+// 128 B per vertex); "feature tiles" later run the dense chain on 32 of them, so
+// no dense work is wasted on part-filled tiles.  The kernel is persistent: warps
+// draw tasks from an atomic counter, heavy and light tasks alternately, so that
+// bandwidth-bound gathers and FMA-bound dense tiles overlap on every SM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,32 +47,27 @@ namespace gvc {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kCtaThreads = kWarpsPerCta * 32;
+#ifndef GVC_CTAS_PER_SM
+#define GVC_CTAS_PER_SM 3
+#endif
+constexpr int kCtasPerSm = GVC_CTAS_PER_SM;
 constexpr int kTileVerts = 32;            // vertices per warp tile
 constexpr int kTileStride = 36;           // floats per k-row of a tile (32 + 4 pad, keeps float4 alignment)
 constexpr int kTileRows = 32;             // widest activation
 constexpr int kTileFloats = kTileRows * kTileStride;
+constexpr int kWarpSmemFloats = kTileFloats + 32;   // tile + vid[32]
 
-// ---- schedule: which vertices a warp tile holds --------------------------------------
-// Real graphs are skewed (the R-MAT benchmark graph: 40 % isolated vertices, 64 % of the
-// adjacency in vertices of degree > 256, one of degree 64 452) and the reference's sums
-// are sequential per vertex, so the critical path is the largest vertex.  At graph upload
-// the vertices are counting-sorted by degree bin (descending) into `order`, and cut into
-// four classes with different tile shapes:
-//   class 0  deg >= 4096        1 vertex  per tile, warp-cooperative gather
-//   class 1  deg in [1024,4096) 4 vertices per tile, warp-cooperative gather
-//   class 2  deg in [256,1024)  16 vertices per tile, warp-cooperative gather
-//   class 3  deg < 256          32 vertices per tile, 4 lanes per vertex (1 lane for w=1)
-// Heavy tiles come first (longest-processing-time-first); class-3 tiles are dealt
-// alternately from the heavy and the light end so that gather-bound and compute-bound
-// tiles share an SM at any time.  Results do not depend on the schedule.
-constexpr int kNumClasses = 4;
-__host__ __device__ constexpr uint32_t class_min_deg(int c) { return c == 0 ? 4096u : c == 1 ? 1024u : c == 2 ? 256u : 0u; }
-__host__ __device__ constexpr int class_verts(int c) { return c == 0 ? 1 : c == 1 ? 4 : c == 2 ? 16 : 32; }
+constexpr uint32_t kRingMinDeg = 2048;    // >= : ring task (whole CTA)
+constexpr uint32_t kCoopMinDeg = 64;      // >= : coop task (one warp per vertex), below: 32-vertex tiles
 constexpr int kNumDegBins = 132;
 
-struct TileTable {
-    uint32_t first_tile[kNumClasses + 1];   // tile index where class c starts; [4] = total tiles
-    uint32_t first_pos[kNumClasses + 1];    // position in `order` where class c starts; [4] = n_local
+// Task layout of one shard, positions refer to `order` (vertices sorted by degree bin, descending).
+struct Schedule {
+    uint32_t n_local;       // vertices of the shard
+    uint32_t n_ring;        // order[0, n_ring)                ring tasks
+    uint32_t n_coop;        // order[n_ring, n_ring + n_coop)  coop tasks
+    uint32_t n_tiles;       // 32-vertex tiles over order[n_ring + n_coop, n_local)
+    uint32_t n_feat_tiles;  // 32-vertex feature tiles over order[0, n_ring + n_coop)
 };
 
 // degree -> bin, monotone in the degree, 4 bins per octave
@@ -67,7 +79,7 @@ __host__ __device__ __forceinline__ int degree_bin(uint32_t d) {
     int lg = 31;
     while (!(d >> lg)) --lg;
 #endif
-    return 4 * lg + (int)((d >> (lg - 2)) & 3u) - 4;   // d=4 -> 4, contiguous from there; max 4*31+3-4 = 123
+    return 4 * lg + (int)((d >> (lg - 2)) & 3u) - 4;   // d=4 -> 4, contiguous from there; max 123
 }
 
 // Packed parameter block of one stage, in floats:
@@ -85,6 +97,7 @@ __host__ __device__ constexpr StageDims stage_dims(int stage) {
          : stage == 1 ? StageDims{32, 32, 32, 32, 32, 16}
                       : StageDims{32, 32, 32, 16, 16, 1};
 }
+__host__ __device__ constexpr int stage_feat_width(int stage) { return stage == 0 ? 5 : 32; }
 
 __device__ __forceinline__ float relu_ref(float v) { return v < 0.0f ? 0.0f : v; }   // std::max(x, 0.0f), :46
 
@@ -96,7 +109,14 @@ __device__ __forceinline__ float mac(float a, float w, float acc) {
 
 __device__ __forceinline__ float4 ldg_row4(const float4 *p) { return __ldg(p); }
 
-// ---- phase B: one dense layer + bias + ReLU over the warp's tile, in place -----
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---- dense: one layer + bias + ReLU over the warp's tile, in place ----------------
 // T: k-major tile, T[k * kTileStride + i], i = vertex in tile.  Lane (og, vg)
 // owns vertices 4vg..4vg+3 and outputs C*og..C*og+C-1.
 template <int K, int NOUT, bool EXACT>
@@ -188,10 +208,37 @@ __device__ __forceinline__ float sigmoid_ref(float v) {
     else return 1.0f / (1.0f + expf(-v));
 }
 
-// ---- phase A, width 16, class 3: 4 lanes per vertex, 8 vertices per pass ----------------
+// The dense chain of one stage over a filled tile, and the store.
+template <int STAGE, bool EXACT>
+__device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const uint32_t *__restrict__ vid,
+                                                     int count, const float *__restrict__ P,
+                                                     float *__restrict__ out, uint32_t v_begin, int lane) {
+    constexpr StageDims D = stage_dims(STAGE);
+    const float *Wa = P, *ba = Wa + D.Ka * D.Na;
+    const float *Wb = ba + D.Na, *bb = Wb + D.Kb * D.Nb;
+    const float *Wc = bb + D.Nb, *bc = Wc + D.Kc * D.Nc;
+    tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane);
+    tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane);
+    if constexpr (STAGE < 2) {
+        tile_linear_relu_store16<D.Kc, EXACT>(T, Wc, bc, lane, out, vid, count);
+    } else {
+        // 16 -> 1: one lane per vertex.  OpenBLAS' 1-column kernel: even/odd
+        // accumulators, C = even + odd (oracle/gnn_oracle.c dot_two_acc).
+        float ev = 0.0f, od = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            ev = mac<EXACT>(T[k * kTileStride + lane], Wc[k], ev);
+            od = mac<EXACT>(T[(k + 1) * kTileStride + lane], Wc[k + 1], od);
+        }
+        const float s = __fadd_rn(__fadd_rn(ev, od), bc[0]);
+        if (lane < count) out[vid[lane] - v_begin] = sigmoid_ref<EXACT>(s);
+    }
+    __syncwarp();
+}
+
+// ---- gather, width 16, tiles (deg < 64): 4 lanes per vertex, 8 vertices per pass ----------
 // vid[i] receives the GLOBAL id of the vertex in slot i.
-template <bool EXACT>
-__device__ __forceinline__ void gather16_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
+__device__ __noinline__ void gather16_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
                                               const uint32_t *__restrict__ order, uint32_t pos0, int count,
                                               const uint32_t *__restrict__ row_ptr,
                                               const uint32_t *__restrict__ col,
@@ -246,133 +293,8 @@ __device__ __forceinline__ void gather16_tile(float *__restrict__ T, uint32_t *_
     __syncwarp();
 }
 
-// ---- phase A, width 16, classes 0-2: the whole warp gathers ONE vertex -------------------
-// 64 neighbour rows per batch: every lane fetches 8 x 16 B (8 rows per load wave, fully
-// coalesced per row), the next batch is in flight while the current one is summed.  The
-// sum itself is the reference's sequential chain: rows are parked in the warp's tile
-// buffer and lane c (< 16) adds column c in adjacency order, 4 cycles per neighbour.
-// Returns acc[c] in lanes 0..15.
-struct BatchIds { uint32_t lo, hi; };   // lane l holds neighbour ids e0+l and e0+32+l
-
-__device__ __forceinline__ BatchIds coop_load_ids(const uint32_t *__restrict__ col, uint32_t e0, uint32_t end,
-                                                  int lane) {
-    BatchIds b;
-    b.lo = (e0 + lane < end) ? __ldg(col + e0 + lane) : 0u;
-    b.hi = (e0 + 32 + lane < end) ? __ldg(col + e0 + 32 + lane) : 0u;
-    return b;
-}
-
-__device__ __forceinline__ void coop_load_rows16(float4 (&r)[8], const BatchIds ids,
-                                                 const float4 *__restrict__ in4, uint32_t e0, uint32_t end,
-                                                 int lane) {
-    const int sv = lane >> 2, q = lane & 3;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const int j = 8 * w + sv;
-        const uint32_t id = __shfl_sync(0xffffffffu, (w < 4) ? ids.lo : ids.hi, j & 31);
-        r[w] = (e0 + j < end) ? ldg_row4(in4 + (size_t)id * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
-// Software pipeline per 64-neighbour batch b: ids of b+2 and rows of b+1 are in flight
-// while batch b is summed (the warp issues in order, so a load must never be consumed in
-// the iteration that issued it).
-__device__ __forceinline__ float coop_gather16(float *__restrict__ S /* >= 1024 floats */,
-                                               const uint32_t *__restrict__ col,
-                                               const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
-                                               int lane) {
-    const int sv = lane >> 2, q = lane & 3;
-    const int c = lane & 15;
-    float acc = 0.0f;
-    if (beg >= end) return acc;
-    float4 cur[8], nxt[8];
-    BatchIds ids0 = coop_load_ids(col, beg, end, lane);
-    BatchIds ids1 = coop_load_ids(col, beg + 64, end, lane);
-    coop_load_rows16(cur, ids0, in4, beg, end, lane);
-#pragma unroll 1
-    for (uint32_t e = beg; e < end; e += 64) {
-        const bool more = e + 64 < end;            // warp-uniform
-        if (more) coop_load_rows16(nxt, ids1, in4, e + 64, end, lane);
-        ids1 = coop_load_ids(col, e + 128, end, lane);
-#pragma unroll
-        for (int w = 0; w < 8; ++w)
-            *reinterpret_cast<float4 *>(S + (8 * w + sv) * 16 + 4 * q) = cur[w];
-        __syncwarp();
-        const int cnt = (int)min(64u, end - e);
-        const float *s = S + c;
-        if (cnt == 64) {
-            float va[16], vb[16];
-#pragma unroll
-            for (int t = 0; t < 16; ++t) va[t] = s[t * 16];
-#pragma unroll
-            for (int g = 0; g < 4; g += 2) {
-#pragma unroll
-                for (int t = 0; t < 16; ++t) vb[t] = s[((g + 1) * 16 + t) * 16];
-#pragma unroll
-                for (int t = 0; t < 16; ++t) acc = __fadd_rn(acc, va[t]);
-                if (g + 2 < 4) {
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) va[t] = s[((g + 2) * 16 + t) * 16];
-                }
-#pragma unroll
-                for (int t = 0; t < 16; ++t) acc = __fadd_rn(acc, vb[t]);
-            }
-        } else {
-            for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, s[j * 16]);
-        }
-        __syncwarp();
-        if (more) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) cur[w] = nxt[w];
-        }
-    }
-    return acc;
-}
-
-// Classes 0-2 tile: `count` vertices, one after the other, each gathered by the whole warp.
-// The gather uses the tile buffer as staging, so the feature columns are collected in
-// registers first (lane c < 16 keeps agg[c] of vertex i in slot register i ... too many
-// registers for 16 vertices) -- instead features go to the upper half of the buffer:
-// staging = floats [0, 1024), feature columns are written after the gather of each vertex
-// into a side strip F (kWarpFeat floats) and copied into the tile at the end.
-template <bool EXACT>
-__device__ __forceinline__ void gather16_coop_tile(float *__restrict__ T, float *__restrict__ F,
-                                                   uint32_t *__restrict__ vid,
-                                                   const uint32_t *__restrict__ order, uint32_t pos0, int count,
-                                                   const uint32_t *__restrict__ row_ptr,
-                                                   const uint32_t *__restrict__ col,
-                                                   const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
-                                                   const float *__restrict__ in, uint32_t v_begin, float scale,
-                                                   int lane) {
-    const float4 *in4 = reinterpret_cast<const float4 *>(in);
-#pragma unroll 1
-    for (int i = 0; i < count; ++i) {
-        const uint32_t ul = __ldg(order + pos0 + i);
-        const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-        const float acc = coop_gather16(T, col, in4, beg, end, lane);
-        // feature vector of vertex i -> F[i][0..32): lanes 0-15 agg, lanes 16-31 self (+ quirk)
-        float f;
-        if (lane < 16) {
-            f = acc;
-        } else {
-            const int c = lane - 16;
-            f = __ldg(in + (size_t)(v_begin + ul) * 16 + c);
-            if (c == 1) f = __uint2float_rn(end - beg);
-            if (c == 2) f = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
-            if (c == 3) f = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
-        }
-        F[i * 32 + lane] = f;
-        if (lane == 0) vid[i] = v_begin + ul;
-    }
-    __syncwarp();
-    // F[i][k] -> T[k][i]; unused slots are zero-filled (their results are never stored)
-    for (int i = 0; i < kTileVerts; ++i)
-        T[lane * kTileStride + i] = (i < count) ? F[i * 32 + lane] : 0.0f;
-    __syncwarp();
-}
-
-// ---- phase A, width 1, class 3: one lane per vertex -------------------------------------------
-__device__ __forceinline__ void gather1_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
+// ---- gather, width 1, tiles: one lane per vertex -------------------------------------------
+__device__ __noinline__ void gather1_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
                                              const uint32_t *__restrict__ order, uint32_t pos0, int count,
                                              const uint32_t *__restrict__ row_ptr,
                                              const uint32_t *__restrict__ col,
@@ -413,19 +335,143 @@ __device__ __forceinline__ void gather1_tile(float *__restrict__ T, uint32_t *__
     __syncwarp();
 }
 
-// ---- phase A, width 1, classes 0-2: the whole warp gathers ONE vertex ---------------------------
-// 32 neighbours per load (coalesced ids, gathered x), two loads ahead; the sequential sum
-// walks the 32 values with shuffles (every lane keeps the same running sum).
-__device__ __forceinline__ float coop_gather1(const uint32_t *__restrict__ col, const float *__restrict__ x,
+// ---- batches of the cooperative gathers (coop and ring tasks) --------------------------------
+struct BatchIds { uint32_t lo, hi; };   // lane l holds neighbour ids e0+l and e0+32+l
+
+__device__ __forceinline__ BatchIds coop_load_ids(const uint32_t *__restrict__ col, uint32_t e0, uint32_t end,
+                                                  int lane) {
+    BatchIds b;
+    b.lo = (e0 + lane < end) ? __ldg(col + e0 + lane) : 0u;
+    b.hi = (e0 + 32 + lane < end) ? __ldg(col + e0 + 32 + lane) : 0u;
+    return b;
+}
+
+// 64 neighbour rows: every lane fetches 8 x 16 B (8 rows per load wave, each row coalesced)
+__device__ __forceinline__ void coop_load_rows16(float4 (&r)[8], const BatchIds ids,
+                                                 const float4 *__restrict__ in4, uint32_t e0, uint32_t end,
+                                                 int lane) {
+    const int sv = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int j = 8 * w + sv;
+        const uint32_t id = __shfl_sync(0xffffffffu, (w < 4) ? ids.lo : ids.hi, j & 31);
+        r[w] = (e0 + j < end) ? ldg_row4(in4 + (size_t)id * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+__device__ __forceinline__ void coop_stage_rows16(float *__restrict__ S, const float4 (&r)[8], int lane) {
+    const int sv = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) *reinterpret_cast<float4 *>(S + (8 * w + sv) * 16 + 4 * q) = r[w];
+}
+
+// The reference's sequential chain over the rows parked in S: lane c (< 16, mirrored in
+// lanes 16..31) adds column c in adjacency order, one dependent FADD per neighbour.
+__device__ __forceinline__ float chain_add16(const float *__restrict__ S, int cnt, float acc, int lane) {
+    const float *s = S + (lane & 15);
+    if (cnt == 64) {
+        // groups of 8 rows, the next group's shared-memory loads overlap the current adds
+        float va[8], vb[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) va[t] = s[t * 16];
+#pragma unroll
+        for (int g = 0; g < 8; g += 2) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) vb[t] = s[((g + 1) * 8 + t) * 16];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, va[t]);
+            if (g + 2 < 8) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) va[t] = s[((g + 2) * 8 + t) * 16];
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, vb[t]);
+        }
+    } else {
+        for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, s[j * 16]);
+    }
+    return acc;
+}
+
+// coop task, width 16.  Software pipeline per 64-neighbour batch b: ids of b+2 and rows of
+// b+1 are in flight while batch b is summed (the warp issues in order, so a load must
+// never be consumed in the iteration that issued it).  Returns acc[c] in lanes c and c+16.
+__device__ __noinline__ float coop_gather16(float *__restrict__ S /* >= 1024 floats */,
+                                               const uint32_t *__restrict__ col,
+                                               const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
+                                               int lane) {
+    float acc = 0.0f;
+    if (beg >= end) return acc;
+    float4 cur[8], nxt[8];
+    BatchIds ids0 = coop_load_ids(col, beg, end, lane);
+    BatchIds ids1 = coop_load_ids(col, beg + 64, end, lane);
+    coop_load_rows16(cur, ids0, in4, beg, end, lane);
+#pragma unroll 1
+    for (uint32_t e = beg; e < end; e += 64) {
+        const bool more = e + 64 < end;            // warp-uniform
+        coop_stage_rows16(S, cur, lane);           // `cur` is dead from here: its registers serve `nxt`
+        if (more) coop_load_rows16(nxt, ids1, in4, e + 64, end, lane);
+        ids1 = coop_load_ids(col, e + 128, end, lane);
+        __syncwarp();
+        acc = chain_add16(S, (int)min(64u, end - e), acc, lane);
+        __syncwarp();
+        if (more) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) cur[w] = nxt[w];
+        }
+    }
+    return acc;
+}
+
+// ring task, width 16: the 8 warps of the CTA serve one vertex.  Warp w fetches batches
+// w, w+8, ... (64 rows each) into its own tile buffer; the running sum travels from warp
+// to warp through shared memory, the hand-over for batch b is named barrier 1 + b % 8
+// (arrive by the warp that summed b-1, sync by the warp that sums b).  All 8 warps call
+// this; the caller reads the 16 sums from ring_acc after a __syncthreads().
+__device__ __noinline__ void ring_gather16(float *__restrict__ S, float *__restrict__ ring_acc,
+                                              const uint32_t *__restrict__ col,
+                                              const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
+                                              int warp, int lane) {
+    const uint32_t nb = (end - beg + 63) / 64;
+    float4 r[8];
+    uint32_t b = warp;
+    BatchIds ids = coop_load_ids(col, beg + 64 * b, end, lane);
+#pragma unroll 1
+    for (; b < nb; b += kWarpsPerCta) {
+        const uint32_t e0 = beg + 64 * b;
+        coop_load_rows16(r, ids, in4, e0, end, lane);
+        ids = coop_load_ids(col, e0 + 64 * kWarpsPerCta, end, lane);   // this warp's next batch
+        coop_stage_rows16(S, r, lane);
+        __syncwarp();
+        float acc = 0.0f;
+        if (b > 0) {
+            named_bar_sync(1 + (int)(b % kWarpsPerCta), 64);
+            acc = ring_acc[lane & 15];
+        }
+        acc = chain_add16(S, (int)min(64u, end - e0), acc, lane);
+        __syncwarp();
+        if (lane < 16) ring_acc[lane] = acc;
+        if (b + 1 < nb) named_bar_arrive(1 + (int)((b + 1) % kWarpsPerCta), 64);
+    }
+}
+
+// ---- width 1 ---------------------------------------------------------------------------------------
+// coop task, width 1: 32 neighbours per load (coalesced ids, gathered x); the sequential sum
+// walks the 32 values with shuffles (every lane keeps the same running sum).  Pipeline per
+// batch b: ids of b+3..b+6 and values of b+1..b+2 in flight.
+__device__ __noinline__ float coop_gather1(const uint32_t *__restrict__ col, const float *__restrict__ x,
                                               uint32_t beg, uint32_t end, int lane) {
     float acc = 0.0f;
     if (beg >= end) return acc;
     auto ld_id = [&](uint32_t e0) { return (e0 + lane < end) ? __ldg(col + e0 + lane) : 0u; };
     auto ld_x = [&](uint32_t id, uint32_t e0) { return (e0 + lane < end) ? __ldg(x + id) : 0.0f; };
-    // pipeline per 32-neighbour batch b: ids of b+3..b+6 and values of b+1..b+2 in flight
-    uint32_t i0 = ld_id(beg), i1 = ld_id(beg + 32), i2 = ld_id(beg + 64), i3 = ld_id(beg + 96),
-             i4 = ld_id(beg + 128), i5 = ld_id(beg + 160);
-    float v0 = ld_x(i0, beg), v1 = ld_x(i1, beg + 32);
+    uint32_t i2, i3, i4, i5;
+    float v0, v1;
+    {
+        const uint32_t i0 = ld_id(beg), i1 = ld_id(beg + 32);
+        i2 = ld_id(beg + 64); i3 = ld_id(beg + 96); i4 = ld_id(beg + 128); i5 = ld_id(beg + 160);
+        v0 = ld_x(i0, beg); v1 = ld_x(i1, beg + 32);
+    }
 #pragma unroll 1
     for (uint32_t e = beg; e < end; e += 32) {
         const float v2 = ld_x(i2, e + 64);
@@ -443,117 +489,188 @@ __device__ __forceinline__ float coop_gather1(const uint32_t *__restrict__ col, 
     return acc;
 }
 
-__device__ __forceinline__ void gather1_coop_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
-                                                  const uint32_t *__restrict__ order, uint32_t pos0, int count,
-                                                  const uint32_t *__restrict__ row_ptr,
-                                                  const uint32_t *__restrict__ col,
-                                                  const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
-                                                  const float *__restrict__ x, uint32_t v_begin, float scale,
-                                                  int lane) {
-    float f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};    // lane i keeps the features of slot i
+// ring task, width 1: warp w sums segments w, w+8, ... of 256 neighbours (8 loads of 32),
+// same hand-over as ring_gather16; the running sum is ring_acc[0].
+__device__ __noinline__ void ring_gather1(float *__restrict__ ring_acc, const uint32_t *__restrict__ col,
+                                             const float *__restrict__ x, uint32_t beg, uint32_t end,
+                                             int warp, int lane) {
+    const uint32_t ns = (end - beg + 255) / 256;
 #pragma unroll 1
-    for (int i = 0; i < count; ++i) {
-        const uint32_t ul = __ldg(order + pos0 + i);
-        const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-        const float acc = coop_gather1(col, x, beg, end, lane);
-        if (lane == i) {
-            f[0] = acc;
-            f[1] = __ldg(x + v_begin + ul);
-            f[2] = __uint2float_rn(end - beg);
-            f[3] = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
-            f[4] = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
-            vid[i] = v_begin + ul;
-        }
-    }
+    for (uint32_t b = warp; b < ns; b += kWarpsPerCta) {
+        const uint32_t e0 = beg + 256 * b;
+        float v[8];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) T[k * kTileStride + lane] = f[k];
-    __syncwarp();
+        for (int t = 0; t < 8; ++t) {
+            const uint32_t e = e0 + 32 * t + lane;
+            v[t] = (e < end) ? __ldg(x + __ldg(col + e)) : 0.0f;
+        }
+        float acc = 0.0f;
+        if (b > 0) {
+            named_bar_sync(1 + (int)(b % kWarpsPerCta), 64);
+            acc = ring_acc[0];
+        }
+        const int cnt = (int)min(256u, end - e0);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int c = min(32, cnt - 32 * t);
+            if (c == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v[t], j));
+            } else {
+                for (int j = 0; j < c; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v[t], j));
+            }
+        }
+        if (lane == 0) ring_acc[0] = acc;
+        if (b + 1 < ns) named_bar_arrive(1 + (int)((b + 1) % kWarpsPerCta), 64);
+    }
 }
 
-// ---- the fused stage kernel ------------------------------------------------------
-// STAGE 0: in = x [n_global], out = h rows [n_global x 16]
+// ---- feature vectors of ring/coop vertices: feat[pos * 32 + k] ------------------------------------
+// width 16: lanes 0-15 hold agg[c], lanes 16-31 supply self[c] with the :38-40 quirk
+__device__ __forceinline__ void put_features16(float *__restrict__ feat, uint32_t pos, float acc,
+                                               const float *__restrict__ in, uint32_t ul, uint32_t deg,
+                                               const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+                                               uint32_t v_begin, float scale, int lane) {
+    float f = acc;
+    if (lane >= 16) {
+        const int c = lane - 16;
+        f = __ldg(in + (size_t)(v_begin + ul) * 16 + c);
+        if (c == 1) f = __uint2float_rn(deg);
+        if (c == 2) f = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
+        if (c == 3) f = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
+    }
+    __stcg(feat + (size_t)pos * 32 + lane, f);
+}
+
+__device__ __forceinline__ void put_features1(float *__restrict__ feat, uint32_t pos, float acc,
+                                              const float *__restrict__ x, uint32_t ul, uint32_t deg,
+                                              const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+                                              uint32_t v_begin, float scale, int lane) {
+    float f = acc;                                                          // [agg | x | D | W/s | NW/s]
+    if (lane == 1) f = __ldg(x + v_begin + ul);
+    if (lane == 2) f = __uint2float_rn(deg);
+    if (lane == 3) f = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
+    if (lane == 4) f = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
+    if (lane < 5) __stcg(feat + (size_t)pos * 32 + lane, f);
+}
+
+// one more feature vector of feature tile pos/32 is complete (release)
+__device__ __forceinline__ void publish_feature(uint32_t *__restrict__ ready, uint32_t pos, int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        atomicAdd(ready + (pos >> 5), 1u);
+    }
+}
+
+// ---- the fused stage kernel (persistent) --------------------------------------------------------------
+// STAGE 0: in = x [n_global],      out = h rows [n_global x 16]
 // STAGE 1: in = h [n_global x 16], out = h rows [n_global x 16]
 // STAGE 2: in = h [n_global x 16], out = scores [n_local]
-constexpr int kWarpFeat = 16 * 32;                                   // side strip F of the cooperative tiles
-constexpr int kWarpSmemFloats = kTileFloats + kWarpFeat + 32;        // tile + F + vid
-
+// sync[0] = task counter, sync[1 + t] = finished feature vectors of feature tile t; zeroed before launch.
 template <int STAGE, bool EXACT>
-__global__ void __launch_bounds__(kCtaThreads, 3)
+__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
              const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
-             const uint32_t *__restrict__ order, const TileTable tt,
-             const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ params,
-             uint32_t v_begin, float scale) {
+             const uint32_t *__restrict__ order, const Schedule sc, float *__restrict__ feat,
+             uint32_t *__restrict__ sync, const float *__restrict__ in, float *__restrict__ out,
+             const float *__restrict__ params, uint32_t v_begin, float scale) {
     constexpr StageDims D = stage_dims(STAGE);
     extern __shared__ __align__(16) float smem[];
     float *P = smem;                                             // packed parameters
     constexpr int kParamFloats = (D.floats() + 3) / 4 * 4;
-    float *warp_mem = smem + kParamFloats;
+    float *ring_acc = smem + kParamFloats;                       // 16 floats
+    float *warp_mem = ring_acc + 16;
 
     for (int i = threadIdx.x; i < D.floats(); i += kCtaThreads) P[i] = __ldg(params + i);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t t = blockIdx.x * kWarpsPerCta + warp;
-    if (t >= tt.first_tile[kNumClasses]) return;
     float *T = warp_mem + warp * kWarpSmemFloats;
-    float *F = T + kTileFloats;
-    uint32_t *vid = reinterpret_cast<uint32_t *>(F + kWarpFeat);
+    uint32_t *vid = reinterpret_cast<uint32_t *>(T + kTileFloats);
+    uint32_t *ready = sync + 1;
 
-    // tile -> class, position range
-    int cls = 0;
-#pragma unroll
-    for (int c = 1; c < kNumClasses; ++c) cls += (t >= tt.first_tile[c]) ? 1 : 0;
-    uint32_t lt = t - tt.first_tile[cls];
-    const int vpt = class_verts(cls);
-    if (cls == kNumClasses - 1) {     // deal class-3 tiles alternately from the heavy and the light end
-        const uint32_t nt = tt.first_tile[kNumClasses] - tt.first_tile[cls];
-        lt = (lt & 1u) ? nt - 1 - (lt >> 1) : (lt >> 1);
-    }
-    const uint32_t pos0 = tt.first_pos[cls] + lt * (uint32_t)vpt;
-    const int count = (int)min((uint32_t)vpt, tt.first_pos[cls + 1] - pos0);
-
-    const float *Wa = P, *ba = Wa + D.Ka * D.Na;
-    const float *Wb = ba + D.Na, *bb = Wb + D.Kb * D.Nb;
-    const float *Wc = bb + D.Nb, *bc = Wc + D.Kc * D.Nc;
-
-    if constexpr (STAGE == 0) {
-        if (cls == kNumClasses - 1)
-            gather1_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);
-        else
-            gather1_coop_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);
-    } else {
-        if (cls == kNumClasses - 1)
-            gather16_tile<EXACT>(T, vid, order, pos0, count, row_ptr, col, Wv, NWv,
-                                 reinterpret_cast<const float4 *>(in), v_begin, scale, lane);
-        else
-            gather16_coop_tile<EXACT>(T, F, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);
-    }
-
-    if constexpr (STAGE < 2) {
-        tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane);
-        tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane);
-        tile_linear_relu_store16<D.Kc, EXACT>(T, Wc, bc, lane, out, vid, count);
-    } else {
-        tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane);
-        tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane);
-        // 16 -> 1: one lane per vertex.  OpenBLAS' 1-column kernel: even/odd
-        // accumulators, C = even + odd (oracle/gnn_oracle.c dot_two_acc).
-        float ev = 0.0f, od = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-            ev = mac<EXACT>(T[k * kTileStride + lane], Wc[k], ev);
-            od = mac<EXACT>(T[(k + 1) * kTileStride + lane], Wc[k + 1], od);
+    // ---- ring tasks: the whole CTA, largest vertices first -------------------------------------
+#pragma unroll 1
+    for (uint32_t g = blockIdx.x; g < sc.n_ring; g += gridDim.x) {
+        const uint32_t ul = __ldg(order + g);
+        const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+        if constexpr (STAGE == 0) ring_gather1(ring_acc, col, in, beg, end, warp, lane);
+        else ring_gather16(T, ring_acc, col, reinterpret_cast<const float4 *>(in), beg, end, warp, lane);
+        __syncthreads();
+        if (warp == 0) {
+            if constexpr (STAGE == 0)
+                put_features1(feat, g, ring_acc[0], in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+            else
+                put_features16(feat, g, ring_acc[lane & 15], in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+            publish_feature(ready, g, lane);
         }
-        const float s = __fadd_rn(__fadd_rn(ev, od), bc[0]);
-        if (lane < count) out[vid[lane] - v_begin] = sigmoid_ref<EXACT>(s);
+        __syncthreads();
+    }
+
+    // ---- dynamic tasks, one warp each ----------------------------------------------------------------
+    const uint32_t n_heavy = sc.n_coop + sc.n_tiles;        // dealt alternately from both ends
+    const uint32_t n_tasks = n_heavy + sc.n_feat_tiles;
+    const uint32_t n_pre = sc.n_ring + sc.n_coop;           // positions that go through feature tiles
+#pragma unroll 1
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(sync, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_tasks) break;
+        if (k < n_heavy) {
+            const uint32_t g = (k & 1u) ? n_heavy - 1 - (k >> 1) : (k >> 1);
+            if (g < sc.n_coop) {
+                // coop task: one vertex, the whole warp
+                const uint32_t pos = sc.n_ring + g;
+                const uint32_t ul = __ldg(order + pos);
+                const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+                if constexpr (STAGE == 0) {
+                    const float acc = coop_gather1(col, in, beg, end, lane);
+                    put_features1(feat, pos, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+                } else {
+                    const float acc = coop_gather16(T, col, reinterpret_cast<const float4 *>(in), beg, end, lane);
+                    put_features16(feat, pos, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+                }
+                publish_feature(ready, pos, lane);
+            } else {
+                // 32-vertex tile: gather + dense + store
+                const uint32_t pos0 = n_pre + (g - sc.n_coop) * kTileVerts;
+                const int count = (int)min((uint32_t)kTileVerts, sc.n_local - pos0);
+                if constexpr (STAGE == 0)
+                    gather1_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);
+                else
+                    gather16_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv,
+                                  reinterpret_cast<const float4 *>(in), v_begin, scale, lane);
+                tile_dense_and_store<STAGE, EXACT>(T, vid, count, P, out, v_begin, lane);
+            }
+        } else {
+            // feature tile: 32 precomputed feature vectors -> dense + store
+            const uint32_t ft = k - n_heavy;
+            const uint32_t pos0 = ft * kTileVerts;
+            const int count = (int)min((uint32_t)kTileVerts, n_pre - pos0);
+            if (lane == 0) {
+                while (*reinterpret_cast<volatile uint32_t *>(ready + ft) < (uint32_t)count) __nanosleep(200);
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane < count) vid[lane] = v_begin + __ldg(order + pos0 + lane);
+            constexpr int FW = stage_feat_width(STAGE);
+            if (lane < FW) {
+#pragma unroll 4
+                for (int i = 0; i < kTileVerts; ++i)
+                    T[lane * kTileStride + i] = (i < count) ? __ldcg(feat + (size_t)(pos0 + i) * 32 + lane) : 0.0f;
+            }
+            __syncwarp();
+            tile_dense_and_store<STAGE, EXACT>(T, vid, count, P, out, v_begin, lane);
+        }
     }
 }
 
 template <int STAGE>
 constexpr size_t stage_smem_bytes() {
     constexpr StageDims D = stage_dims(STAGE);
-    return ((D.floats() + 3) / 4 * 4 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
+    return ((D.floats() + 3) / 4 * 4 + 16 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
 }
 
 // ---- schedule construction (graph upload time) -------------------------------------------

@@ -48,9 +48,13 @@ namespace gvc {
 constexpr int kWarpsPerCta = 8;
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 #ifndef GVC_CTAS_PER_SM
-#define GVC_CTAS_PER_SM 3
+#define GVC_CTAS_PER_SM 2
+#endif
+#ifndef GVC_DENSE_UNROLL
+#define GVC_DENSE_UNROLL 2      // k-steps per loop body: small bodies keep the dense code in the instruction cache
 #endif
 constexpr int kCtasPerSm = GVC_CTAS_PER_SM;
+constexpr int kDenseUnroll = GVC_DENSE_UNROLL;
 constexpr int kTileVerts = 32;            // vertices per warp tile
 constexpr int kTileStride = 36;           // floats per k-row of a tile (32 + 4 pad, keeps float4 alignment)
 constexpr int kTileRows = 32;             // widest activation
@@ -131,7 +135,7 @@ __device__ __forceinline__ void tile_linear_relu(float *__restrict__ T, const fl
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[r][c] = 0.0f;
 
-#pragma unroll 8
+#pragma unroll kDenseUnroll
     for (int k = 0; k < K; ++k) {
         const float4 a = *reinterpret_cast<const float4 *>(T + k * kTileStride + 4 * vg);
         float w[C];
@@ -175,7 +179,7 @@ __device__ __forceinline__ void tile_linear_relu_store16(const float *__restrict
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
-#pragma unroll 8
+#pragma unroll kDenseUnroll
     for (int k = 0; k < K; ++k) {
         const float4 a = *reinterpret_cast<const float4 *>(T + k * kTileStride + 4 * vg);
         const float4 ww = *reinterpret_cast<const float4 *>(Wsm + k * 16 + 4 * og);

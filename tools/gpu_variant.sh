@@ -5,7 +5,7 @@ GVC_NVCC_EXTRA="$*" python -c "
 import sys; sys.path.insert(0,'.')
 import gnn_mwvc_b200
 from gnn_mwvc_b200 import build
-build.build_libgvc(force=True)"
+build.build_libgvc(force=True)" || { echo BUILD FAILED; exit 1; }
 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err || tail -5 gpurun_out/bench_${tag}.err
 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --mode fast > gpurun_out/bench_${tag}_fast.json 2>> gpurun_out/bench_${tag}.err
 python - <<PY

@@ -255,19 +255,21 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     const uint32_t nl = c->n_local();
     if (nl == 0) return 0;
     const Schedule &sc = c->sched;
-    const uint32_t n_tasks = sc.n_coop + sc.n_tiles + sc.n_feat_tiles;
+    const uint32_t n_tasks = (sc.n_coop + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
     const unsigned want = std::max<unsigned>(sc.n_ring, (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
     const unsigned grid = std::max(1u, std::min<unsigned>(kCtasPerSm * c->num_sms, want));
+    Schedule sc_launch = sc;
+    sc_launch.n_ring_ctas = std::min<unsigned>(grid, (unsigned)c->num_sms);   // one ring CTA per SM at most
     const size_t smem = stage_smem_bytes<STAGE>();
     // task counter + per-feature-tile completion counters start at zero
     GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (1 + (size_t)sc.n_feat_tiles) * sizeof(uint32_t), c->stream));
     if (mode == GVC_MODE_EXACT) {
         stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, sc, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
             c->d_stage_params[STAGE], c->v_begin, scale);
     } else {
         stage_kernel<STAGE, false><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, sc, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
             c->d_stage_params[STAGE], c->v_begin, scale);
     }
     GVC_CUDA(cudaGetLastError());

@@ -29,10 +29,10 @@
 //                         fetches every 8th 64-row batch, the running sum is
 //                         handed from warp to warp through named barriers, so
 //                         512 rows are in flight for a single sequential chain
-//   coop    64 <= deg     one warp per vertex, 64 rows in flight, next batch's
-//           < 2048        rows and the batch after's ids prefetched
+//   mid     64 <= deg     8 vertices per warp task, 4 lanes per vertex, 16 rows in
+//           < 2048        flight per vertex (w=1: one vertex at a time, whole warp)
 //   tile    deg < 64      32 vertices per warp, 4 lanes per vertex (1 for w=1)
-// ring and coop tasks only produce the 32-float feature vector (side buffer,
+// ring and mid tasks only produce the 32-float feature vector (side buffer,
 // 128 B per vertex); "feature tiles" later run the dense chain on 32 of them, so
 // no dense work is wasted on part-filled tiles.  The kernel is persistent: warps
 // draw tasks from an atomic counter, heavy and light tasks alternately, so that
@@ -69,7 +69,8 @@ constexpr int kNumDegBins = 132;
 struct Schedule {
     uint32_t n_local;       // vertices of the shard
     uint32_t n_ring;        // order[0, n_ring)                ring tasks
-    uint32_t n_coop;        // order[n_ring, n_ring + n_coop)  coop tasks
+    uint32_t n_coop;        // order[n_ring, n_ring + n_coop)  mid-degree vertices, 8 per task
+    uint32_t n_ring_ctas;   // CTAs [0, n_ring_ctas) share the ring tasks before joining the task queue
     uint32_t n_tiles;       // 32-vertex tiles over order[n_ring + n_coop, n_local)
     uint32_t n_feat_tiles;  // 32-vertex feature tiles over order[0, n_ring + n_coop)
 };
@@ -240,9 +241,73 @@ __device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const u
     __syncwarp();
 }
 
-// ---- gather, width 16, tiles (deg < 64): 4 lanes per vertex, 8 vertices per pass ----------
-// vid[i] receives the GLOBAL id of the vertex in slot i.
-__device__ __noinline__ void gather16_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
+// ---- gather, width 16: 4 lanes per vertex ------------------------------------------------------
+// One sub-warp (lanes 4s..4s+3, lane q holds floats 4q..4q+3 of every row) sums the rows of
+// one vertex in adjacency order.  Chunks of kChunk neighbours; the ids of chunks k+1 and k+2 and
+// the rows of chunk k+1 are in flight while chunk k is added (in-order issue: a load is never
+// consumed in the phase that issued it).  Two register sets alternate.
+#ifndef GVC_GATHER_CHUNK
+#define GVC_GATHER_CHUNK 4
+#endif
+constexpr int kChunk = GVC_GATHER_CHUNK;
+
+__device__ __forceinline__ void load_ids(uint32_t (&id)[kChunk], const uint32_t *__restrict__ col, uint32_t e,
+                                         uint32_t end) {
+#pragma unroll
+    for (int t = 0; t < kChunk; ++t) id[t] = (e + t < end) ? __ldg(col + e + t) : 0u;
+}
+__device__ __forceinline__ void load_rows(float4 (&r)[kChunk], const uint32_t (&id)[kChunk],
+                                          const float4 *__restrict__ in4, int q, uint32_t e, uint32_t end) {
+#pragma unroll
+    for (int t = 0; t < kChunk; ++t)
+        if (e + t < end) r[t] = ldg_row4(in4 + (size_t)id[t] * 4 + q);
+}
+__device__ __forceinline__ void add_rows(float4 &acc, const float4 (&r)[kChunk], uint32_t e, uint32_t end) {
+#pragma unroll
+    for (int t = 0; t < kChunk; ++t)
+        if (e + t < end) {
+            acc.x = __fadd_rn(acc.x, r[t].x); acc.y = __fadd_rn(acc.y, r[t].y);
+            acc.z = __fadd_rn(acc.z, r[t].z); acc.w = __fadd_rn(acc.w, r[t].w);
+        }
+}
+
+__device__ __forceinline__ float4 gather16_vertex(const uint32_t *__restrict__ col,
+                                                  const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
+                                                  int q) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beg >= end) return acc;
+    uint32_t idA[kChunk], idB[kChunk];
+    float4 rA[kChunk], rB[kChunk];
+    load_ids(idA, col, beg, end);
+    load_ids(idB, col, beg + kChunk, end);
+    load_rows(rA, idA, in4, q, beg, end);
+    for (uint32_t e = beg; e < end; e += 2 * kChunk) {
+        load_rows(rB, idB, in4, q, e + kChunk, end);
+        load_ids(idA, col, e + 2 * kChunk, end);
+        add_rows(acc, rA, e, end);
+        if (e + kChunk >= end) break;
+        load_rows(rA, idA, in4, q, e + 2 * kChunk, end);
+        load_ids(idB, col, e + 3 * kChunk, end);
+        add_rows(acc, rB, e + kChunk, end);
+    }
+    return acc;
+}
+
+// self features with the :38-40 quirk: D, W/s, NW/s overwrite self features 1..3
+__device__ __forceinline__ float4 self_features16(const float4 *__restrict__ in4, uint32_t ul, uint32_t deg,
+                                                  const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+                                                  uint32_t v_begin, float scale, int q) {
+    float4 self = ldg_row4(in4 + (size_t)(v_begin + ul) * 4 + q);                     // :37
+    if (q == 0) {
+        self.y = __uint2float_rn(deg);
+        self.z = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
+        self.w = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
+    }
+    return self;
+}
+
+// tiles (deg < 64): 8 vertices per pass, 4 passes; vid[i] receives the GLOBAL id of slot i.
+__device__ __forceinline__ void gather16_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
                                               const uint32_t *__restrict__ order, uint32_t pos0, int count,
                                               const uint32_t *__restrict__ row_ptr,
                                               const uint32_t *__restrict__ col,
@@ -257,37 +322,10 @@ __device__ __noinline__ void gather16_tile(float *__restrict__ T, uint32_t *__re
         float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < count) {
             const uint32_t ul = __ldg(order + pos0 + i);
-            uint32_t e = __ldg(row_ptr + ul);
-            const uint32_t end = __ldg(row_ptr + ul + 1);
-            const uint32_t deg = end - e;
-            // ids are fetched one iteration ahead of the rows they address, so the two
-            // dependent load latencies (col -> row) overlap instead of adding up
-            uint32_t id[8], nid[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) id[t] = (e + t < end) ? __ldg(col + e + t) : 0u;
-            for (; e < end; e += 8) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) nid[t] = (e + 8 + t < end) ? __ldg(col + e + 8 + t) : 0u;
-                float4 r[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (e + t < end) r[t] = ldg_row4(in4 + (size_t)id[t] * 4 + q);
-#pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (e + t < end) {
-                        acc.x = __fadd_rn(acc.x, r[t].x); acc.y = __fadd_rn(acc.y, r[t].y);
-                        acc.z = __fadd_rn(acc.z, r[t].z); acc.w = __fadd_rn(acc.w, r[t].w);
-                    }
-#pragma unroll
-                for (int t = 0; t < 8; ++t) id[t] = nid[t];
-            }
-            self = ldg_row4(in4 + (size_t)(v_begin + ul) * 4 + q);                     // :37
-            if (q == 0) {   // the quirk: D, W/s, NW/s overwrite self features 1..3 (:38-40)
-                self.y = __uint2float_rn(deg);
-                self.z = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
-                self.w = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
-                vid[i] = v_begin + ul;
-            }
+            const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+            acc = gather16_vertex(col, in4, beg, end, q);
+            self = self_features16(in4, ul, end - beg, Wv, NWv, v_begin, scale, q);
+            if (q == 0) vid[i] = v_begin + ul;
         }
         float *t = T + (4 * q) * kTileStride + i;
         t[0] = acc.x; t[kTileStride] = acc.y; t[2 * kTileStride] = acc.z; t[3 * kTileStride] = acc.w;
@@ -295,6 +333,31 @@ __device__ __noinline__ void gather16_tile(float *__restrict__ T, uint32_t *__re
         t[0] = self.x; t[kTileStride] = self.y; t[2 * kTileStride] = self.z; t[3 * kTileStride] = self.w;
     }
     __syncwarp();
+}
+
+// mid task (64 <= deg < 2048): 8 vertices, one per sub-warp; the feature vectors go to the
+// side buffer (128 B per vertex, two 64 B halves written by the 4 lanes of the sub-warp).
+__device__ __forceinline__ void gather16_mid_task(float *__restrict__ feat, uint32_t *__restrict__ ready,
+                                               const uint32_t *__restrict__ order, uint32_t pos0, int count,
+                                               const uint32_t *__restrict__ row_ptr,
+                                               const uint32_t *__restrict__ col,
+                                               const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+                                               const float4 *__restrict__ in4, uint32_t v_begin, float scale,
+                                               int lane) {
+    const int sv = lane >> 2, q = lane & 3;
+    if (sv < count) {
+        const uint32_t pos = pos0 + sv;
+        const uint32_t ul = __ldg(order + pos);
+        const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+        const float4 acc = gather16_vertex(col, in4, beg, end, q);
+        const float4 self = self_features16(in4, ul, end - beg, Wv, NWv, v_begin, scale, q);
+        float4 *f = reinterpret_cast<float4 *>(feat + (size_t)pos * 32);
+        __stcg(f + q, acc);
+        __stcg(f + 4 + q, self);
+        __threadfence();
+    }
+    __syncwarp();
+    if (sv < count && q == 0) atomicAdd(ready + ((pos0 + sv) >> 5), 1u);
 }
 
 // ---- gather, width 1, tiles: one lane per vertex -------------------------------------------
@@ -393,36 +456,6 @@ __device__ __forceinline__ float chain_add16(const float *__restrict__ S, int cn
         }
     } else {
         for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, s[j * 16]);
-    }
-    return acc;
-}
-
-// coop task, width 16.  Software pipeline per 64-neighbour batch b: ids of b+2 and rows of
-// b+1 are in flight while batch b is summed (the warp issues in order, so a load must
-// never be consumed in the iteration that issued it).  Returns acc[c] in lanes c and c+16.
-__device__ __noinline__ float coop_gather16(float *__restrict__ S /* >= 1024 floats */,
-                                               const uint32_t *__restrict__ col,
-                                               const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
-                                               int lane) {
-    float acc = 0.0f;
-    if (beg >= end) return acc;
-    float4 cur[8], nxt[8];
-    BatchIds ids0 = coop_load_ids(col, beg, end, lane);
-    BatchIds ids1 = coop_load_ids(col, beg + 64, end, lane);
-    coop_load_rows16(cur, ids0, in4, beg, end, lane);
-#pragma unroll 1
-    for (uint32_t e = beg; e < end; e += 64) {
-        const bool more = e + 64 < end;            // warp-uniform
-        coop_stage_rows16(S, cur, lane);           // `cur` is dead from here: its registers serve `nxt`
-        if (more) coop_load_rows16(nxt, ids1, in4, e + 64, end, lane);
-        ids1 = coop_load_ids(col, e + 128, end, lane);
-        __syncwarp();
-        acc = chain_add16(S, (int)min(64u, end - e), acc, lane);
-        __syncwarp();
-        if (more) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) cur[w] = nxt[w];
-        }
     }
     return acc;
 }
@@ -560,11 +593,9 @@ __device__ __forceinline__ void put_features1(float *__restrict__ feat, uint32_t
 
 // one more feature vector of feature tile pos/32 is complete (release)
 __device__ __forceinline__ void publish_feature(uint32_t *__restrict__ ready, uint32_t pos, int lane) {
+    __threadfence();
     __syncwarp();
-    if (lane == 0) {
-        __threadfence();
-        atomicAdd(ready + (pos >> 5), 1u);
-    }
+    if (lane == 0) atomicAdd(ready + (pos >> 5), 1u);
 }
 
 // ---- the fused stage kernel (persistent) --------------------------------------------------------------
@@ -596,7 +627,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
 
     // ---- ring tasks: the whole CTA, largest vertices first -------------------------------------
 #pragma unroll 1
-    for (uint32_t g = blockIdx.x; g < sc.n_ring; g += gridDim.x) {
+    for (uint32_t g = blockIdx.x; blockIdx.x < sc.n_ring_ctas && g < sc.n_ring; g += sc.n_ring_ctas) {
         const uint32_t ul = __ldg(order + g);
         const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
         if constexpr (STAGE == 0) ring_gather1(ring_acc, col, in, beg, end, warp, lane);
@@ -613,7 +644,8 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     }
 
     // ---- dynamic tasks, one warp each ----------------------------------------------------------------
-    const uint32_t n_heavy = sc.n_coop + sc.n_tiles;        // dealt alternately from both ends
+    const uint32_t n_mid = (sc.n_coop + 7) / 8;              // mid tasks, 8 vertices each
+    const uint32_t n_heavy = n_mid + sc.n_tiles;            // dealt alternately from both ends
     const uint32_t n_tasks = n_heavy + sc.n_feat_tiles;
     const uint32_t n_pre = sc.n_ring + sc.n_coop;           // positions that go through feature tiles
 #pragma unroll 1
@@ -624,22 +656,27 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
         if (k >= n_tasks) break;
         if (k < n_heavy) {
             const uint32_t g = (k & 1u) ? n_heavy - 1 - (k >> 1) : (k >> 1);
-            if (g < sc.n_coop) {
-                // coop task: one vertex, the whole warp
-                const uint32_t pos = sc.n_ring + g;
-                const uint32_t ul = __ldg(order + pos);
-                const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+            if (g < n_mid) {
+                const uint32_t pos0 = sc.n_ring + 8 * g;
+                const int count = (int)min(8u, n_pre - pos0);
                 if constexpr (STAGE == 0) {
-                    const float acc = coop_gather1(col, in, beg, end, lane);
-                    put_features1(feat, pos, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+                    // w = 1: the 8 vertices one after the other, the whole warp on each
+#pragma unroll 1
+                    for (int i = 0; i < count; ++i) {
+                        const uint32_t pos = pos0 + i;
+                        const uint32_t ul = __ldg(order + pos);
+                        const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+                        const float acc = coop_gather1(col, in, beg, end, lane);
+                        put_features1(feat, pos, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+                        publish_feature(ready, pos, lane);
+                    }
                 } else {
-                    const float acc = coop_gather16(T, col, reinterpret_cast<const float4 *>(in), beg, end, lane);
-                    put_features16(feat, pos, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+                    gather16_mid_task(feat, ready, order, pos0, count, row_ptr, col, Wv, NWv,
+                                      reinterpret_cast<const float4 *>(in), v_begin, scale, lane);
                 }
-                publish_feature(ready, pos, lane);
             } else {
                 // 32-vertex tile: gather + dense + store
-                const uint32_t pos0 = n_pre + (g - sc.n_coop) * kTileVerts;
+                const uint32_t pos0 = n_pre + (g - n_mid) * kTileVerts;
                 const int count = (int)min((uint32_t)kTileVerts, sc.n_local - pos0);
                 if constexpr (STAGE == 0)
                     gather1_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);

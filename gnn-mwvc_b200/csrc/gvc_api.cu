@@ -255,8 +255,9 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     const uint32_t nl = c->n_local();
     if (nl == 0) return 0;
     const Schedule &sc = c->sched;
-    const uint32_t n_tasks = (sc.n_coop + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
-    const unsigned want = std::max<unsigned>(sc.n_ring, (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
+    const uint32_t n_tasks = STAGE == 0 ? sc.n_ring + (nl - sc.n_ring + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
+                                        : (sc.n_coop + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
+    const unsigned want = std::max<unsigned>(STAGE == 0 ? 0u : sc.n_ring, (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
     const unsigned grid = std::max(1u, std::min<unsigned>(kCtasPerSm * c->num_sms, want));
     Schedule sc_launch = sc;
     sc_launch.n_ring_ctas = std::min<unsigned>(grid, (unsigned)c->num_sms);   // one ring CTA per SM at most

@@ -493,73 +493,49 @@ __device__ __noinline__ void ring_gather16(float *__restrict__ S, float *__restr
 }
 
 // ---- width 1 ---------------------------------------------------------------------------------------
-// coop task, width 1: 32 neighbours per load (coalesced ids, gathered x); the sequential sum
-// walks the 32 values with shuffles (every lane keeps the same running sum).  Pipeline per
-// batch b: ids of b+3..b+6 and values of b+1..b+2 in flight.
+// single-warp task, width 1 (stage 0 giants): blocks of 256 neighbours, lane l holds elements
+// 32 t + l (coalesced ids, gathered x).  The ids of block b+2 and the values of block b+1 are
+// in flight while block b is summed; the sequential sum walks the values with shuffles (every
+// lane keeps the same running sum), ~1150 cycles per block, which covers the memory latency.
 __device__ __noinline__ float coop_gather1(const uint32_t *__restrict__ col, const float *__restrict__ x,
                                               uint32_t beg, uint32_t end, int lane) {
     float acc = 0.0f;
     if (beg >= end) return acc;
-    auto ld_id = [&](uint32_t e0) { return (e0 + lane < end) ? __ldg(col + e0 + lane) : 0u; };
-    auto ld_x = [&](uint32_t id, uint32_t e0) { return (e0 + lane < end) ? __ldg(x + id) : 0.0f; };
-    uint32_t i2, i3, i4, i5;
-    float v0, v1;
-    {
-        const uint32_t i0 = ld_id(beg), i1 = ld_id(beg + 32);
-        i2 = ld_id(beg + 64); i3 = ld_id(beg + 96); i4 = ld_id(beg + 128); i5 = ld_id(beg + 160);
-        v0 = ld_x(i0, beg); v1 = ld_x(i1, beg + 32);
-    }
-#pragma unroll 1
-    for (uint32_t e = beg; e < end; e += 32) {
-        const float v2 = ld_x(i2, e + 64);
-        const uint32_t i6 = ld_id(e + 192);
-        const int cnt = (int)min(32u, end - e);
-        if (cnt == 32) {
+    uint32_t idn[8], idnn[8];
+    float v[8], vn[8];
+    auto ld_ids = [&](uint32_t (&id)[8], uint32_t e0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v0, j));
-        } else {
-            for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v0, j));
-        }
-        v0 = v1; v1 = v2;
-        i2 = i3; i3 = i4; i4 = i5; i5 = i6;
-    }
-    return acc;
-}
-
-// ring task, width 1: warp w sums segments w, w+8, ... of 256 neighbours (8 loads of 32),
-// same hand-over as ring_gather16; the running sum is ring_acc[0].
-__device__ __noinline__ void ring_gather1(float *__restrict__ ring_acc, const uint32_t *__restrict__ col,
-                                             const float *__restrict__ x, uint32_t beg, uint32_t end,
-                                             int warp, int lane) {
-    const uint32_t ns = (end - beg + 255) / 256;
-#pragma unroll 1
-    for (uint32_t b = warp; b < ns; b += kWarpsPerCta) {
-        const uint32_t e0 = beg + 256 * b;
-        float v[8];
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < end) ? __ldg(col + e) : 0u; }
+    };
+    auto ld_x = [&](float (&val)[8], const uint32_t (&id)[8], uint32_t e0) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const uint32_t e = e0 + 32 * t + lane;
-            v[t] = (e < end) ? __ldg(x + __ldg(col + e)) : 0.0f;
-        }
-        float acc = 0.0f;
-        if (b > 0) {
-            named_bar_sync(1 + (int)(b % kWarpsPerCta), 64);
-            acc = ring_acc[0];
-        }
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; val[t] = (e < end) ? __ldg(x + id[t]) : 0.0f; }
+    };
+    ld_ids(idn, beg);
+    ld_ids(idnn, beg + 256);
+    ld_x(v, idn, beg);
+    ld_ids(idn, beg + 512);                       // idn: block 2, idnn: block 1
+#pragma unroll 1
+    for (uint32_t e0 = beg; e0 < end; e0 += 256) {
+        ld_x(vn, idnn, e0 + 256);                 // values of the next block
+#pragma unroll
+        for (int t = 0; t < 8; ++t) idnn[t] = idn[t];
+        ld_ids(idn, e0 + 768);                    // ids two blocks further
         const int cnt = (int)min(256u, end - e0);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const int c = min(32, cnt - 32 * t);
-            if (c == 32) {
+            const int c = cnt - 32 * t;
+            if (c >= 32) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v[t], j));
             } else {
                 for (int j = 0; j < c; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v[t], j));
             }
         }
-        if (lane == 0) ring_acc[0] = acc;
-        if (b + 1 < ns) named_bar_arrive(1 + (int)((b + 1) % kWarpsPerCta), 64);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = vn[t];
     }
+    return acc;
 }
 
 // ---- feature vectors of ring/coop vertices: feat[pos * 32 + k] ------------------------------------
@@ -625,29 +601,32 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     uint32_t *vid = reinterpret_cast<uint32_t *>(T + kTileFloats);
     uint32_t *ready = sync + 1;
 
-    // ---- ring tasks: the whole CTA, largest vertices first -------------------------------------
+    // ---- ring tasks (width 16 only): the whole CTA, largest vertices first --------------------
+    // With w = 1 the chain costs the same 4 cycles per neighbour whoever feeds it and one warp
+    // can keep its own loads ahead, so stage 0 runs the giants as single-warp tasks instead.
+    if constexpr (STAGE != 0) {
 #pragma unroll 1
-    for (uint32_t g = blockIdx.x; blockIdx.x < sc.n_ring_ctas && g < sc.n_ring; g += sc.n_ring_ctas) {
-        const uint32_t ul = __ldg(order + g);
-        const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-        if constexpr (STAGE == 0) ring_gather1(ring_acc, col, in, beg, end, warp, lane);
-        else ring_gather16(T, ring_acc, col, reinterpret_cast<const float4 *>(in), beg, end, warp, lane);
-        __syncthreads();
-        if (warp == 0) {
-            if constexpr (STAGE == 0)
-                put_features1(feat, g, ring_acc[0], in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
-            else
+        for (uint32_t g = blockIdx.x; blockIdx.x < sc.n_ring_ctas && g < sc.n_ring; g += sc.n_ring_ctas) {
+            const uint32_t ul = __ldg(order + g);
+            const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+            ring_gather16(T, ring_acc, col, reinterpret_cast<const float4 *>(in), beg, end, warp, lane);
+            __syncthreads();
+            if (warp == 0) {
                 put_features16(feat, g, ring_acc[lane & 15], in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
-            publish_feature(ready, g, lane);
+                publish_feature(ready, g, lane);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     // ---- dynamic tasks, one warp each ----------------------------------------------------------------
-    const uint32_t n_mid = (sc.n_coop + 7) / 8;              // mid tasks, 8 vertices each
-    const uint32_t n_heavy = n_mid + sc.n_tiles;            // dealt alternately from both ends
-    const uint32_t n_tasks = n_heavy + sc.n_feat_tiles;
-    const uint32_t n_pre = sc.n_ring + sc.n_coop;           // positions that go through feature tiles
+    // stage 0: front = the giants, one warp each; everything else is a 32-vertex tile.
+    // stages 1/2: front = mid tasks (8 vertices each); tiles hold the vertices of degree < 64.
+    const uint32_t n_pre = STAGE == 0 ? sc.n_ring : sc.n_ring + sc.n_coop;   // positions that go through feature tiles
+    const uint32_t n_front = STAGE == 0 ? sc.n_ring : (sc.n_coop + 7) / 8;
+    const uint32_t n_tiles = (sc.n_local - n_pre + kTileVerts - 1) / kTileVerts;
+    const uint32_t n_heavy = n_front + n_tiles;             // dealt alternately from both ends
+    const uint32_t n_tasks = n_heavy + (n_pre + kTileVerts - 1) / kTileVerts;
 #pragma unroll 1
     for (;;) {
         uint32_t k = 0;
@@ -656,27 +635,21 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
         if (k >= n_tasks) break;
         if (k < n_heavy) {
             const uint32_t g = (k & 1u) ? n_heavy - 1 - (k >> 1) : (k >> 1);
-            if (g < n_mid) {
-                const uint32_t pos0 = sc.n_ring + 8 * g;
-                const int count = (int)min(8u, n_pre - pos0);
+            if (g < n_front) {
                 if constexpr (STAGE == 0) {
-                    // w = 1: the 8 vertices one after the other, the whole warp on each
-#pragma unroll 1
-                    for (int i = 0; i < count; ++i) {
-                        const uint32_t pos = pos0 + i;
-                        const uint32_t ul = __ldg(order + pos);
-                        const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-                        const float acc = coop_gather1(col, in, beg, end, lane);
-                        put_features1(feat, pos, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
-                        publish_feature(ready, pos, lane);
-                    }
+                    const uint32_t ul = __ldg(order + g);
+                    const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+                    const float acc = coop_gather1(col, in, beg, end, lane);
+                    put_features1(feat, g, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+                    publish_feature(ready, g, lane);
                 } else {
-                    gather16_mid_task(feat, ready, order, pos0, count, row_ptr, col, Wv, NWv,
+                    const uint32_t pos0 = sc.n_ring + 8 * g;
+                    gather16_mid_task(feat, ready, order, pos0, (int)min(8u, n_pre - pos0), row_ptr, col, Wv, NWv,
                                       reinterpret_cast<const float4 *>(in), v_begin, scale, lane);
                 }
             } else {
                 // 32-vertex tile: gather + dense + store
-                const uint32_t pos0 = n_pre + (g - n_mid) * kTileVerts;
+                const uint32_t pos0 = n_pre + (g - n_front) * kTileVerts;
                 const int count = (int)min((uint32_t)kTileVerts, sc.n_local - pos0);
                 if constexpr (STAGE == 0)
                     gather1_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);

@@ -495,9 +495,11 @@ __device__ __noinline__ void ring_gather16(float *__restrict__ S, float *__restr
 // ---- width 1 ---------------------------------------------------------------------------------------
 // single-warp task, width 1 (stage 0 giants): blocks of 256 neighbours, lane l holds elements
 // 32 t + l (coalesced ids, gathered x).  The ids of block b+2 and the values of block b+1 are
-// in flight while block b is summed; the sequential sum walks the values with shuffles (every
-// lane keeps the same running sum), ~1150 cycles per block, which covers the memory latency.
-__device__ __noinline__ float coop_gather1(const uint32_t *__restrict__ col, const float *__restrict__ x,
+// in flight while block b is summed.  The block is parked in shared memory and every lane
+// walks it with broadcast 128-bit loads (one dependent FADD per neighbour, ~4 cycles), which
+// covers the memory latency of the next block.
+__device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 floats */,
+                                              const uint32_t *__restrict__ col, const float *__restrict__ x,
                                               uint32_t beg, uint32_t end, int lane) {
     float acc = 0.0f;
     if (beg >= end) return acc;
@@ -517,21 +519,25 @@ __device__ __noinline__ float coop_gather1(const uint32_t *__restrict__ col, con
     ld_ids(idn, beg + 512);                       // idn: block 2, idnn: block 1
 #pragma unroll 1
     for (uint32_t e0 = beg; e0 < end; e0 += 256) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) S[32 * t + lane] = v[t];
         ld_x(vn, idnn, e0 + 256);                 // values of the next block
 #pragma unroll
         for (int t = 0; t < 8; ++t) idnn[t] = idn[t];
         ld_ids(idn, e0 + 768);                    // ids two blocks further
+        __syncwarp();
         const int cnt = (int)min(256u, end - e0);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int c = cnt - 32 * t;
-            if (c >= 32) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v[t], j));
-            } else {
-                for (int j = 0; j < c; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v[t], j));
-            }
+        const float4 *s4 = reinterpret_cast<const float4 *>(S);
+        int j = 0;
+        for (; j + 16 <= cnt; j += 16) {
+            const float4 a = s4[j / 4], b = s4[j / 4 + 1], c = s4[j / 4 + 2], d = s4[j / 4 + 3];
+            acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
+            acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y); acc = __fadd_rn(acc, b.z); acc = __fadd_rn(acc, b.w);
+            acc = __fadd_rn(acc, c.x); acc = __fadd_rn(acc, c.y); acc = __fadd_rn(acc, c.z); acc = __fadd_rn(acc, c.w);
+            acc = __fadd_rn(acc, d.x); acc = __fadd_rn(acc, d.y); acc = __fadd_rn(acc, d.z); acc = __fadd_rn(acc, d.w);
         }
+        for (; j < cnt; ++j) acc = __fadd_rn(acc, S[j]);
+        __syncwarp();
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[t] = vn[t];
     }
@@ -639,7 +645,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
                 if constexpr (STAGE == 0) {
                     const uint32_t ul = __ldg(order + g);
                     const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-                    const float acc = coop_gather1(col, in, beg, end, lane);
+                    const float acc = coop_gather1(T, col, in, beg, end, lane);
                     put_features1(feat, g, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
                     publish_feature(ready, g, lane);
                 } else {

@@ -45,7 +45,10 @@
 
 namespace gvc {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef GVC_WARPS_PER_CTA
+#define GVC_WARPS_PER_CTA 8
+#endif
+constexpr int kWarpsPerCta = GVC_WARPS_PER_CTA;   // <= 15 (ring hand-over uses named barriers 1..kWarpsPerCta)
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 #ifndef GVC_CTAS_PER_SM
 #define GVC_CTAS_PER_SM 2
@@ -61,8 +64,14 @@ constexpr int kTileRows = 32;             // widest activation
 constexpr int kTileFloats = kTileRows * kTileStride;
 constexpr int kWarpSmemFloats = kTileFloats + 32;   // tile + vid[32]
 
-constexpr uint32_t kRingMinDeg = 2048;    // >= : ring task (whole CTA)
-constexpr uint32_t kCoopMinDeg = 64;      // >= : coop task (one warp per vertex), below: 32-vertex tiles
+#ifndef GVC_RING_MIN_DEG
+#define GVC_RING_MIN_DEG 2048
+#endif
+#ifndef GVC_MID_MIN_DEG
+#define GVC_MID_MIN_DEG 64
+#endif
+constexpr uint32_t kRingMinDeg = GVC_RING_MIN_DEG;    // >= : ring task (whole CTA)
+constexpr uint32_t kCoopMinDeg = GVC_MID_MIN_DEG;      // >= : coop task (one warp per vertex), below: 32-vertex tiles
 constexpr int kNumDegBins = 132;
 
 // Task layout of one shard, positions refer to `order` (vertices sorted by degree bin, descending).
@@ -113,6 +122,10 @@ __device__ __forceinline__ float mac(float a, float w, float acc) {
 }
 
 __device__ __forceinline__ float4 ldg_row4(const float4 *p) { return __ldg(p); }
+// neighbour ids are read exactly once: stream them past the caches so they do not evict feature rows
+__device__ __forceinline__ uint32_t ld_id(const uint32_t *p) {
+    return __ldcs(p);
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -254,7 +267,7 @@ constexpr int kChunk = GVC_GATHER_CHUNK;
 __device__ __forceinline__ void load_ids(uint32_t (&id)[kChunk], const uint32_t *__restrict__ col, uint32_t e,
                                          uint32_t end) {
 #pragma unroll
-    for (int t = 0; t < kChunk; ++t) id[t] = (e + t < end) ? __ldg(col + e + t) : 0u;
+    for (int t = 0; t < kChunk; ++t) id[t] = (e + t < end) ? ld_id(col + e + t) : 0u;
 }
 __device__ __forceinline__ void load_rows(float4 (&r)[kChunk], const uint32_t (&id)[kChunk],
                                           const float4 *__restrict__ in4, int q, uint32_t e, uint32_t end) {
@@ -376,10 +389,10 @@ __device__ __noinline__ void gather1_tile(float *__restrict__ T, uint32_t *__res
         fd = __uint2float_rn(end - e);
         uint32_t id[8], nid[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) id[t] = (e + t < end) ? __ldg(col + e + t) : 0u;
+        for (int t = 0; t < 8; ++t) id[t] = (e + t < end) ? ld_id(col + e + t) : 0u;
         for (; e < end; e += 8) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) nid[t] = (e + 8 + t < end) ? __ldg(col + e + 8 + t) : 0u;
+            for (int t = 0; t < 8; ++t) nid[t] = (e + 8 + t < end) ? ld_id(col + e + 8 + t) : 0u;
             float a[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) a[t] = (e + t < end) ? __ldg(x + id[t]) : 0.0f;
@@ -408,8 +421,8 @@ struct BatchIds { uint32_t lo, hi; };   // lane l holds neighbour ids e0+l and e
 __device__ __forceinline__ BatchIds coop_load_ids(const uint32_t *__restrict__ col, uint32_t e0, uint32_t end,
                                                   int lane) {
     BatchIds b;
-    b.lo = (e0 + lane < end) ? __ldg(col + e0 + lane) : 0u;
-    b.hi = (e0 + 32 + lane < end) ? __ldg(col + e0 + 32 + lane) : 0u;
+    b.lo = (e0 + lane < end) ? ld_id(col + e0 + lane) : 0u;
+    b.hi = (e0 + 32 + lane < end) ? ld_id(col + e0 + 32 + lane) : 0u;
     return b;
 }
 
@@ -507,7 +520,7 @@ __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 float
     float v[8], vn[8];
     auto ld_ids = [&](uint32_t (&id)[8], uint32_t e0) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < end) ? __ldg(col + e) : 0u; }
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < end) ? ld_id(col + e) : 0u; }
     };
     auto ld_x = [&](float (&val)[8], const uint32_t (&id)[8], uint32_t e0) {
 #pragma unroll

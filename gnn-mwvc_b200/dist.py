@@ -59,7 +59,14 @@ def exchange_rows(full: torch.Tensor, bounds, group=None) -> None:
         return
     rank = dist.get_rank(group)
     views = [full[bounds[r]:bounds[r + 1]] for r in range(world)]
-    dist.all_gather(views, views[rank], group=group)
+    sizes = {v.shape[0] for v in views}
+    if len(sizes) == 1:
+        dist.all_gather(views, views[rank], group=group)          # equal slices: one collective
+    else:
+        # work-balanced ranges differ in length; one broadcast per owner, in place
+        for r in range(world):
+            if views[r].numel():
+                dist.broadcast(views[r], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
 
 
 def sharded_forward(stage_fn, shard: Shard, x_full: torch.Tensor, h1: torch.Tensor, h2: torch.Tensor,

@@ -259,3 +259,19 @@ def test_full_size_properties(ctx):
     assert rel < FAST_RTOL, rel
     # a sample of vertices recomputed by the oracle-independent per-layer kernels: same bits
     # (two different CUDA implementations of the same operation order must agree)
+
+
+def test_multi_gpu_parity_when_several_gpus_are_visible():
+    """On a box with >= 2 GPUs: N processes over NCCL == 1 GPU, bit for bit (tools/multi_gpu_check.py)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU visible; the sharding is covered by test_shards_are_bit_identical_to_one_gpu "
+                    "and by tests/test_dist_cpu.py (gloo)")
+    n = 2 if n < 4 else 4
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        str(ROOT / "tools" / "multi_gpu_check.py"), "15"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_PARITY ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

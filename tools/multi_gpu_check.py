@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Multi-GPU parity: the sharded forward on N GPUs (one process per GPU, NCCL) must equal the
+single-GPU forward bit for bit.  Launch:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29533 tools/multi_gpu_check.py [rmat_scale]
+Rank 0 prints one line `MULTI_GPU_PARITY ok ...` or raises."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import gnn_mwvc_b200 as pkg  # noqa: E402
+from gnn_mwvc_b200 import capi, graphs  # noqa: E402
+from gnn_mwvc_b200 import dist as gdist  # noqa: E402
+
+
+def main():
+    scale_log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    layers = capi.load_model_npz(ROOT / "tests" / "golden" / "mwvc_model.npz")
+    g = graphs.rmat_graph(scale_log2, 16, seed=7, device=dev, n_limit=(1 << scale_log2) - 3)   # odd vertex count
+    s = 200.0
+    x = (g.weights.to(torch.float32) / s).contiguous()
+    bounds = graphs.nnz_balanced_ranges(g.row_ptr, world)
+    shard = gdist.make_shard(g, bounds, rank)
+    for mode in (pkg.MODE_EXACT, pkg.MODE_FAST):
+        ctx = pkg.Context(local)
+        ctx.model_upload(layers)
+        ctx.graph_adopt(shard.row_ptr.to(torch.int32).contiguous(), shard.col, shard.weights, shard.nw,
+                        n_global=g.n, v_begin=shard.v_begin, v_end=shard.v_end)
+        h1 = torch.zeros(g.n, 16, device=dev)
+        h2 = torch.zeros(g.n, 16, device=dev)
+        sc = torch.zeros(shard.n_local, device=dev)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(ctx.torch_stream()):
+            gdist.sharded_forward(ctx.stage_device, shard, x, h1, h2, sc, s, mode)
+            full = gdist.gather_scores(sc, bounds)
+        torch.cuda.synchronize()
+        # single-GPU forward of the whole graph on every rank
+        one = pkg.Context(local)
+        one.model_upload(layers)
+        one.graph_adopt(g.row_ptr.to(torch.int32).contiguous(), g.col, g.weights, g.nw)
+        ref = torch.zeros(g.n, device=dev)
+        torch.cuda.synchronize()
+        one.forward_device(x, s, ref, mode)
+        one.sync()
+        same = torch.equal(full, ref)
+        t = torch.tensor([int(same)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            assert int(t.item()) == 1, f"mode {mode}: {world}-GPU scores differ from 1-GPU scores"
+        ctx.close()
+        one.close()
+    if rank == 0:
+        print(f"MULTI_GPU_PARITY ok world={world} n={g.n} E={g.n_edges} bounds={bounds}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

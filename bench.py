@@ -211,6 +211,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
@@ -241,7 +242,14 @@ def run_ours(args):
     n, m, e_total = g.n, g.nnz, g.n_edges
     weight_scale = 200.0
     x_full = (g.weights.to(torch.float32) / weight_scale).contiguous()
-    bounds = graphs.nnz_balanced_ranges(g.row_ptr, world) if world > 1 else [0, n]
+    if world > 1:
+        # equal-sized shards of the cyclically relabelled graph: every world-th vertex per shard
+        g, _perm = graphs.cyclic_relabel(g, world)
+        x_full = (g.weights.to(torch.float32) / weight_scale).contiguous()
+        per = g.n // world
+        bounds = [r * per for r in range(world + 1)]
+    else:
+        bounds = [0, n]
     shard = gdist.make_shard(g, bounds, rank)
     rp32 = shard.row_ptr.to(torch.int32).contiguous()
     g.eu = g.ev = None
@@ -249,10 +257,12 @@ def run_ours(args):
 
     ctx = pkg.Context(local_rank)
     ctx.model_upload(layers)
-    ctx.graph_adopt(rp32, shard.col, shard.weights, shard.nw, n_global=n, v_begin=shard.v_begin, v_end=shard.v_end)
+    ctx.graph_adopt(rp32, shard.col, shard.weights, shard.nw, n_global=g.n, v_begin=shard.v_begin, v_end=shard.v_end)
+    if world > 1:
+        ctx.graph_set_tail(int(_perm[n - 1].item()) if n % 2 else None)
     stream = ctx.torch_stream()
-    h1 = torch.zeros(n, 16, device=dev)
-    h2 = torch.zeros(n, 16, device=dev)
+    h1 = torch.zeros(g.n, 16, device=dev)
+    h2 = torch.zeros(g.n, 16, device=dev)
     scores = torch.zeros(shard.n_local, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     torch.cuda.synchronize()
@@ -288,6 +298,24 @@ def run_ours(args):
         step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
         total_ms = float(np.sum(step_ms))
 
+        # ---- multi-GPU: where the step goes (stage kernels vs row exchanges), CUDA events --------
+        phase_ms = None
+        if world > 1:
+            names = ["stage0", "exchange_h1", "stage1", "exchange_h2", "stage2"]
+            acc = {k: [] for k in names}
+            for rep in range(5):
+                flush.fill_(rep)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+                ev[0].record(stream)
+                ctx.stage_device(0, x_full, h1, weight_scale, mode); ev[1].record(stream)
+                gdist.exchange_rows(h1, bounds); ev[2].record(stream)
+                ctx.stage_device(1, h1, h2, weight_scale, mode); ev[3].record(stream)
+                gdist.exchange_rows(h2, bounds); ev[4].record(stream)
+                ctx.stage_device(2, h2, scores, weight_scale, mode); ev[5].record(stream)
+                ev[5].synchronize()
+                for i, k in enumerate(names):
+                    acc[k].append(ev[i].elapsed_time(ev[i + 1]))
+            phase_ms = {k: float(np.median(v)) for k, v in acc.items()}
         # ---- per-stage kernel timing for the roofline (dominant kernel = stage 1) ----------------
         stage_ms = [[], [], []]
         if world == 1:
@@ -377,10 +405,10 @@ def run_ours(args):
             "config": {"workload": wl_name, "vertices": n, "edges": e_total, "nnz": m, "mode": args.mode,
                        "weights": "trained GNN_VC model (tests/golden/mwvc_model.npz)",
                        "l2": "256 MiB flush write between timed steps; working set (CSR + rows) also exceeds the 126 MB L2",
-                       "sharding": "single GPU" if world == 1 else f"{world} work-balanced vertex ranges, NCCL all-gather of 16-float rows after stages 0 and 1",
+                       "sharding": "single GPU" if world == 1 else f"{world} equal vertex ranges of the cyclically relabelled graph (v -> shard v % {world}), NCCL all-gather of 16-float rows after stages 0 and 1",
                        "graph_generation_s": round(gen_s, 2)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "phase_ms": phase_ms,
             "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
         }
         print(json.dumps(line), flush=True)
@@ -408,4 +436,9 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    # skip interpreter teardown: torch would free tensors that were used on the library's stream
+    # after that stream is gone
+    os._exit(rc or 0)

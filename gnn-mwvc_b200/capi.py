@@ -33,6 +33,7 @@ SIGNATURES = {
     "gvc_graph_upload": (C.c_int, [C.c_void_p, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
     "gvc_graph_upload_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
     "gvc_graph_adopt_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gvc_graph_set_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "gvc_forward": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, C.c_int]),
     "gvc_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]),
     "gvc_stage_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "gvc_sgemm_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, _f32p, C.c_uint64,
                                  _f32p, C.c_uint64, C.c_float, _f32p, C.c_uint64]),
     "gvc_stream": (C.c_void_p, [C.c_void_p]),
+    "gvc_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gvc_sync": (C.c_int, [C.c_void_p]),
     "gvc_launch_count": (C.c_uint64, [C.c_void_p]),
     "gvc_debug_h": (C.c_void_p, [C.c_void_p, C.c_int]),
@@ -177,6 +179,14 @@ class Context:
                                                     _dptr(col_i32), _dptr(W_i32), _dptr(NW_i32)))
         self.n_global, self.v_begin, self.v_end = n_global, v_begin, v_end
 
+    def graph_set_tail(self, global_vertex):
+        """Where the reference's last vertex of an odd-sized graph went after a relabelling
+        (None: the graph has an even vertex count, or the vertex lives on another shard)."""
+        if global_vertex is not None and self.v_begin <= global_vertex < self.v_end:
+            self._check(self.lib.gvc_graph_set_tail(self.h, 1, global_vertex - self.v_begin))
+        else:
+            self._check(self.lib.gvc_graph_set_tail(self.h, 0, 0))
+
     # -- forward ---------------------------------------------------------------
     def forward(self, x, weight_scale: float, mode: int = MODE_EXACT) -> np.ndarray:
         """Host in, host out: gnn::model::predict."""
@@ -248,9 +258,18 @@ class Context:
     def stream_ptr(self) -> int:
         return int(self.lib.gvc_stream(self.h) or 0)
 
-    def torch_stream(self):
+    def use_torch_stream(self, stream=None):
+        """Enqueue on a torch stream (default: a new one) and return it; torch copies, NCCL
+        collectives and events issued under ``torch.cuda.stream(s)`` then order with the forward."""
         import torch
-        return torch.cuda.ExternalStream(self.stream_ptr, device=torch.device("cuda", self.device))
+        if stream is None:
+            stream = torch.cuda.Stream(device=torch.device("cuda", self.device))
+        self._check(self.lib.gvc_set_stream(self.h, C.c_void_p(stream.cuda_stream)))
+        self._torch_stream = stream            # keep it alive while it is set
+        return stream
+
+    def torch_stream(self):
+        return self.use_torch_stream(getattr(self, "_torch_stream", None))
 
     def sync(self):
         self._check(self.lib.gvc_sync(self.h))

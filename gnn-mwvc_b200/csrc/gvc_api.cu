@@ -86,7 +86,8 @@ struct PinBuf {   // grow-only pinned host buffer
 
 struct gvc_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // where work is enqueued (own_stream unless gvc_set_stream)
+    cudaStream_t own_stream = nullptr;
     uint64_t launches = 0;
 
     // model
@@ -97,6 +98,8 @@ struct gvc_ctx {
     // graph shard
     bool have_graph = false;
     uint32_t n_global = 0, v_begin = 0, v_end = 0;
+    int tail_override = -1;          // -1: default rule, 0: no tail vertex here, 1: tail_local
+    uint32_t tail_local = 0;
     uint64_t nnz = 0;
     const uint32_t *row_ptr = nullptr, *col = nullptr, *Wv = nullptr, *NWv = nullptr;   // device views
     DevBuf<uint32_t> own_row_ptr, own_col, own_W, own_NW;
@@ -276,9 +279,12 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     GVC_CUDA(cudaGetLastError());
     c->launches++;
     // OpenBLAS' 1-row remainder kernel: last vertex of an odd-sized graph (exact mode only)
-    if (mode == GVC_MODE_EXACT && (c->n_global & 1u) && c->v_end == c->n_global) {
+    const bool default_tail = (c->n_global & 1u) && c->v_end == c->n_global;
+    const bool has_tail = c->tail_override < 0 ? default_tail : c->tail_override == 1;
+    if (mode == GVC_MODE_EXACT && has_tail) {
+        const uint32_t tail = c->tail_override == 1 ? c->tail_local : nl - 1;
         stage_tail_kernel<STAGE><<<1, 32, 0, c->stream>>>(c->row_ptr, c->col, c->Wv, c->NWv, d_in, d_out,
-                                                          c->d_stage_params[STAGE], nl - 1, c->v_begin, scale);
+                                                          c->d_stage_params[STAGE], tail, c->v_begin, scale);
         GVC_CUDA(cudaGetLastError());
         c->launches++;
     }
@@ -412,6 +418,7 @@ int set_graph_views(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_
     c->n_global = n_global; c->v_begin = v_begin; c->v_end = v_end; c->nnz = nnz;
     c->row_ptr = rp; c->col = col; c->Wv = W; c->NWv = NW;
     c->have_graph = true;
+    c->tail_override = -1;
     int rc;
     if ((rc = ensure_activations(c))) return rc;
     return build_schedule(c);
@@ -442,11 +449,12 @@ int gvc_ctx_create(gvc_ctx **out, int device) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     GVC_CUDA(cudaSetDevice(device));
-    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(1000 + (int)e, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    c->stream = c->own_stream;
     int rc;
     if ((rc = set_stage_attrs<0>()) || (rc = set_stage_attrs<1>()) || (rc = set_stage_attrs<2>())) {
-        cudaStreamDestroy(c->stream);
+        cudaStreamDestroy(c->own_stream);
         delete c;
         return rc;
     }
@@ -466,7 +474,7 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
     c->d_ping.release(); c->d_pong.release();
     c->pin_x.release(); c->pin_scores.release();
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -557,6 +565,16 @@ int gvc_graph_adopt_device(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
     if (v_end > v_begin && (!d_row_ptr || !d_W || !d_NW)) return fail(GVC_ERR_ARG, "null graph arrays");
     if ((rc = use_device(c))) return rc;
     return set_graph_views(c, n_global, v_begin, v_end, d_row_ptr, d_col, d_W, d_NW, 0);
+}
+
+int gvc_graph_set_tail(gvc_ctx *c, int has_tail, uint32_t local_index) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!c->have_graph) return fail(GVC_ERR_STATE, "no graph uploaded");
+    if (has_tail && local_index >= c->n_local()) return fail(GVC_ERR_ARG, "tail vertex %u outside the shard", local_index);
+    c->tail_override = has_tail ? 1 : 0;
+    c->tail_local = local_index;
+    return 0;
 }
 
 int gvc_stage_device(gvc_ctx *c, int stage, const float *d_in, float *d_out, float scale, int mode) {
@@ -774,6 +792,15 @@ int gvc_sgemm_host(gvc_ctx *c, int ta, int tb, uint64_t m, uint64_t n, uint64_t 
 }
 
 void *gvc_stream(gvc_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int gvc_set_stream(gvc_ctx *c, void *stream) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if ((rc = use_device(c))) return rc;
+    GVC_CUDA(cudaStreamSynchronize(c->stream));          // nothing of ours may still be in flight on the old one
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return 0;
+}
 
 int gvc_sync(gvc_ctx *c) {
     int rc;

@@ -209,3 +209,37 @@ def nnz_balanced_ranges(row_ptr: torch.Tensor, parts: int, align: int = 32):
         bounds.append(max(i, bounds[-1]))
     bounds.append(n)
     return bounds
+
+
+def cyclic_relabel(g: Graph, parts: int):
+    """Relabel vertex v -> (v % parts) * ceil(n / parts) + v // parts so that contiguous ranges of
+    the new ids hold every parts-th original vertex: equal-sized shards (one NCCL all-gather per
+    exchange instead of per-owner broadcasts) whose work is balanced statistically even when the
+    degree depends on the id (R-MAT).  Adjacency lists keep their order, only the names change,
+    so per-vertex results are bit-identical: scores_new[perm[v]] == scores_old[v].
+    Returns (relabelled graph on ceil(n/parts)*parts ids -- padding vertices are isolated, weight 1 --,
+    perm [n] int64)."""
+    n = g.n
+    per = (n + parts - 1) // parts
+    n_pad = per * parts
+    dev = g.row_ptr.device
+    v = torch.arange(n, dtype=torch.int64, device=dev)
+    perm = (v % parts) * per + v // parts
+    deg = g.row_ptr[1:] - g.row_ptr[:-1]
+    new_deg = torch.zeros(n_pad, dtype=torch.int64, device=dev)
+    new_deg[perm] = deg
+    row_ptr = torch.zeros(n_pad + 1, dtype=torch.int64, device=dev)
+    row_ptr[1:] = torch.cumsum(new_deg, 0)
+    # move every adjacency list to its new place, ids renamed, order kept
+    src_new = torch.repeat_interleave(perm, deg)                    # new owner of every entry (old entry order)
+    within = torch.arange(g.nnz, dtype=torch.int64, device=dev) - torch.repeat_interleave(g.row_ptr[:-1], deg)
+    dst = row_ptr[src_new] + within
+    col_old = g.col.to(torch.int64) & 0xFFFFFFFF
+    col = torch.empty(g.nnz, dtype=torch.int32, device=dev)
+    col[dst] = to_u32(perm[col_old])
+    weights = torch.ones(n_pad, dtype=torch.int32, device=dev)
+    weights[perm] = g.weights
+    nw = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+    nw[perm] = g.nw
+    out = Graph(n=n_pad, row_ptr=row_ptr, col=col, weights=weights, nw=nw, name=g.name + f"_cyc{parts}")
+    return out, perm

@@ -102,6 +102,14 @@ int gvc_graph_adopt_device(gvc_ctx *ctx, uint32_t n_global, uint32_t v_begin, ui
                            const uint32_t *d_row_ptr, const uint32_t *d_col, const uint32_t *d_W,
                            const uint32_t *d_NW);
 
+/* Exact mode reproduces OpenBLAS' 1-row remainder kernel for the LAST vertex of a graph with an
+ * odd vertex count (oracle/gnn_oracle.c).  By default that is vertex n_global - 1 and it is
+ * handled by the shard that owns it.  A caller that renames vertices before sharding
+ * (gnn-mwvc_b200/graphs.py cyclic_relabel) says where that vertex went: has_tail = 0 -> this
+ * shard owns no such vertex, 1 -> it is local vertex `local_index`.  Call after the graph
+ * upload/adopt (which resets to the default). */
+int gvc_graph_set_tail(gvc_ctx *ctx, int has_tail, uint32_t local_index);
+
 /* ---- forward: gnn::model::predict (src/gnn_inference.cpp:67-81) ------------ */
 
 /* Whole forward with HOST buffers: x[n] (= in(u,0), src/GNN_VC.cpp:189-191),
@@ -158,6 +166,11 @@ int gvc_sgemm_host(gvc_ctx *ctx, int trans_a, int trans_b, uint64_t m, uint64_t 
 
 /* The context's CUDA stream as an opaque handle (cudaStream_t). */
 void *gvc_stream(gvc_ctx *ctx);
+/* Make the context enqueue on a caller-owned stream (cudaStream_t of the context's device),
+ * e.g. the host framework's current stream, so that its copies, collectives and events order
+ * with the forward without extra synchronisation.  NULL returns to the context's own stream.
+ * The caller keeps the stream alive while it is set. */
+int gvc_set_stream(gvc_ctx *ctx, void *stream);
 /* Block until everything enqueued on the context's stream has finished. */
 int gvc_sync(gvc_ctx *ctx);
 /* Number of kernels this context has launched so far. */

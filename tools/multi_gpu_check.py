@@ -29,13 +29,35 @@ def main():
     g = graphs.rmat_graph(scale_log2, 16, seed=7, device=dev, n_limit=(1 << scale_log2) - 3)   # odd vertex count
     s = 200.0
     x = (g.weights.to(torch.float32) / s).contiguous()
-    bounds = graphs.nnz_balanced_ranges(g.row_ptr, world)
+    for layout in ("ranges", "cyclic"):
+        run_layout(layout, g, x, s, layers, rank, world, local, dev)
+    if rank == 0:
+        print(f"MULTI_GPU_PARITY ok world={world} n={g.n} E={g.n_edges}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_layout(layout, g0, x0, s, layers, rank, world, local, dev):
+    """ranges: work-balanced contiguous ranges of the original ids (unequal, per-owner broadcasts);
+    cyclic: equal ranges of the cyclically relabelled graph (one all-gather per exchange)."""
+    if layout == "cyclic":
+        g, perm = graphs.cyclic_relabel(g0, world)
+        x = (g.weights.to(torch.float32) / s).contiguous()
+        per = g.n // world
+        bounds = [r * per for r in range(world + 1)]
+        tail = int(perm[g0.n - 1].item()) if g0.n % 2 else None
+    else:
+        g, perm, x = g0, None, x0
+        bounds = graphs.nnz_balanced_ranges(g.row_ptr, world)
+        tail = "default"
     shard = gdist.make_shard(g, bounds, rank)
     for mode in (pkg.MODE_EXACT, pkg.MODE_FAST):
         ctx = pkg.Context(local)
         ctx.model_upload(layers)
         ctx.graph_adopt(shard.row_ptr.to(torch.int32).contiguous(), shard.col, shard.weights, shard.nw,
                         n_global=g.n, v_begin=shard.v_begin, v_end=shard.v_end)
+        if tail != "default":
+            ctx.graph_set_tail(tail)
         h1 = torch.zeros(g.n, 16, device=dev)
         h2 = torch.zeros(g.n, 16, device=dev)
         sc = torch.zeros(shard.n_local, device=dev)
@@ -47,23 +69,23 @@ def main():
         # single-GPU forward of the whole graph on every rank
         one = pkg.Context(local)
         one.model_upload(layers)
-        one.graph_adopt(g.row_ptr.to(torch.int32).contiguous(), g.col, g.weights, g.nw)
-        ref = torch.zeros(g.n, device=dev)
+        one.graph_adopt(g0.row_ptr.to(torch.int32).contiguous(), g0.col, g0.weights, g0.nw)
+        ref = torch.zeros(g0.n, device=dev)
         torch.cuda.synchronize()
-        one.forward_device(x, s, ref, mode)
+        one.forward_device(x0, s, ref, mode)
         one.sync()
-        same = torch.equal(full, ref)
+        same = torch.equal(full[perm] if perm is not None else full, ref)
         t = torch.tensor([int(same)], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:
-            assert int(t.item()) == 1, f"mode {mode}: {world}-GPU scores differ from 1-GPU scores"
+            assert int(t.item()) == 1, f"{layout}, mode {mode}: {world}-GPU scores differ from 1-GPU scores"
+        del h1, h2, sc, full, ref
+        torch.cuda.synchronize()
         ctx.close()
         one.close()
-    if rank == 0:
-        print(f"MULTI_GPU_PARITY ok world={world} n={g.n} E={g.n_edges} bounds={bounds}", flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     main()
+    sys.stdout.flush()
+    os._exit(0)

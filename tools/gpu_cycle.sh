@@ -18,3 +18,8 @@ if [ "$2" = "ncu" ]; then
   ncu --set full --clock-control none --import-source on -k regex:stage_kernel -s 9 -c 3 -o gpurun_out/prof_${tag} python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_${tag}.log 2>&1
   tail -2 gpurun_out/ncu_${tag}.log
 fi
+if [ "$2" = "ncu" ]; then
+  # launch list of the same command (per-launch device time; cold-cache and serialised: compare shares)
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_${tag}.log 2>&1
+  tail -1 gpurun_out/ncu_launches_${tag}.log
+fi

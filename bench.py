@@ -236,6 +236,11 @@ def run_ours(args):
         side = int(round((20_000_000 * world) ** 0.5))
         g = graphs.grid_graph(side, side, device=dev)
         wl_name = f"grid_{side}x{side}"
+    elif args.workload == "isolated":      # dense chain only: no edges at all (diagnostic)
+        nn = (1 << 20) * world
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        g = graphs.graph_from_edges(nn, z, z, graphs.random_weights(nn, 3, dev), name="isolated")
+        wl_name = f"isolated_{nn}"
     else:
         g = graphs.er_graph(10000 * world, 50000 * world, seed=1, device=dev)
         wl_name = f"er_{g.n}_{g.n_edges}"
@@ -335,7 +340,7 @@ def run_ours(args):
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    value = e_total * args.steps / (total_ms * 1e-3)
+    value = max(e_total, 1) * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the host-buffer API ------------------------------------------------
     e2e = None
@@ -348,7 +353,7 @@ def run_ours(args):
         for _ in range(k):
             out_host = ctx.forward(x_host, weight_scale, mode)
         e2e_s = (time.perf_counter() - t1) / k
-        e2e = {"value": e_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * n),
+        e2e = {"value": max(e_total, 1) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * n),
                "d2h_bytes_per_step": int(4 * n), "ms_per_step": e2e_s * 1e3,
                "what": "gvc_forward(): pinned H2D of x, 3 fused kernels, D2H of the scores; CSR resident (uploaded once)"}
         assert np.isfinite(out_host).all()
@@ -425,7 +430,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
-    ap.add_argument("--workload", default="rmat", choices=["rmat", "grid", "er"])
+    ap.add_argument("--workload", default="rmat", choices=["rmat", "grid", "er", "isolated"])
     ap.add_argument("--scale", type=int, default=0, help="override the R-MAT scale")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -106,6 +106,7 @@ struct gvc_ctx {
     PinBuf<uint32_t> stage_u32;
     // schedule (gvc_kernels.cuh): vertices counting-sorted by degree bin + tile classes
     DevBuf<uint32_t> d_order, d_bins, d_sync;
+    DevBuf<uint4> d_vrec;
     DevBuf<float> d_feat;
     gvc::Schedule sched{};
     int num_sms = 148;
@@ -269,11 +270,11 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (1 + (size_t)sc.n_feat_tiles) * sizeof(uint32_t), c->stream));
     if (mode == GVC_MODE_EXACT) {
         stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
             c->d_stage_params[STAGE], c->v_begin, scale);
     } else {
         stage_kernel<STAGE, false><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
             c->d_stage_params[STAGE], c->v_begin, scale);
     }
     GVC_CUDA(cudaGetLastError());
@@ -299,6 +300,7 @@ int build_schedule(gvc_ctx *c) {
     if (nl == 0) return 0;
     int rc;
     if ((rc = c->d_order.reserve(nl))) return rc;
+    if ((rc = c->d_vrec.reserve(nl))) return rc;
     if ((rc = c->d_bins.reserve(kNumDegBins))) return rc;
     GVC_CUDA(cudaMemsetAsync(c->d_bins.p, 0, kNumDegBins * sizeof(uint32_t), c->stream));
     const unsigned grid = std::min<unsigned>(1184, (nl + 255) / 256);
@@ -324,7 +326,7 @@ int build_schedule(gvc_ctx *c) {
     if ((rc = c->d_feat.reserve((size_t)n_pre * 32))) return rc;
     if ((rc = c->d_sync.reserve(1 + (size_t)sc.n_feat_tiles))) return rc;
     GVC_CUDA(cudaMemcpyAsync(c->d_bins.p, start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
-    degree_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, nl, c->d_bins.p, c->d_order.p);
+    degree_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, c->Wv, nl, c->d_bins.p, c->d_order.p, c->d_vrec.p);
     GVC_CUDA(cudaGetLastError());
     c->launches++;
     GVC_CUDA(cudaStreamSynchronize(c->stream));   // `start` lives on this stack frame
@@ -470,7 +472,7 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     for (auto &p : c->d_stage_params) if (p) cudaFree(p);
     c->own_row_ptr.release(); c->own_col.release(); c->own_W.release(); c->own_NW.release();
     c->stage_u32.release();
-    c->d_order.release(); c->d_bins.release(); c->d_sync.release(); c->d_feat.release();
+    c->d_order.release(); c->d_vrec.release(); c->d_bins.release(); c->d_sync.release(); c->d_feat.release();
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
     c->d_ping.release(); c->d_pong.release();
     c->pin_x.release(); c->pin_scores.release();

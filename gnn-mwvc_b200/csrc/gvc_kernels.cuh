@@ -321,29 +321,44 @@ __device__ __forceinline__ float4 self_features16(const float4 *__restrict__ in4
 
 // tiles (deg < 64): 8 vertices per pass, 4 passes; vid[i] receives the GLOBAL id of slot i.
 __device__ __forceinline__ void gather16_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
-                                              const uint32_t *__restrict__ order, uint32_t pos0, int count,
-                                              const uint32_t *__restrict__ row_ptr,
+                                              const uint4 *__restrict__ vrec, uint32_t pos0, int count,
                                               const uint32_t *__restrict__ col,
-                                              const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+                                              const uint32_t *__restrict__ NWv,
                                               const float4 *__restrict__ in4, uint32_t v_begin, float scale,
                                               int lane) {
     const int sv = lane >> 2, q = lane & 3;
-#pragma unroll 1
+    // vertex records {id, row begin, row end, W} of this lane's 4 vertices: one round trip for all
+    // four passes instead of the chain order -> row_ptr -> W per pass
+    uint4 rec[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        rec[p] = (p * 8 + sv < count) ? __ldg(vrec + pos0 + p * 8 + sv) : make_uint4(0u, 0u, 0u, 0u);
+    // self rows and NW of all four passes are requested before the first gather starts
+    float4 self[4];
+    uint32_t nw[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const bool on = p * 8 + sv < count;
+        self[p] = on ? ldg_row4(in4 + (size_t)(v_begin + rec[p].x) * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);   // :37
+        nw[p] = (on && q == 0) ? __ldg(NWv + rec[p].x) : 0u;
+    }
+#pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int i = p * 8 + sv;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < count) {
-            const uint32_t ul = __ldg(order + pos0 + i);
-            const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-            acc = gather16_vertex(col, in4, beg, end, q);
-            self = self_features16(in4, ul, end - beg, Wv, NWv, v_begin, scale, q);
-            if (q == 0) vid[i] = v_begin + ul;
+            acc = gather16_vertex(col, in4, rec[p].y, rec[p].z, q);
+            if (q == 0) {   // the quirk: D, W/s, NW/s overwrite self features 1..3 (:38-40)
+                self[p].y = __uint2float_rn(rec[p].z - rec[p].y);
+                self[p].z = __fdiv_rn(__uint2float_rn(rec[p].w), scale);
+                self[p].w = __fdiv_rn(__uint2float_rn(nw[p]), scale);
+                vid[i] = v_begin + rec[p].x;
+            }
         }
         float *t = T + (4 * q) * kTileStride + i;
         t[0] = acc.x; t[kTileStride] = acc.y; t[2 * kTileStride] = acc.z; t[3 * kTileStride] = acc.w;
         t += 16 * kTileStride;
-        t[0] = self.x; t[kTileStride] = self.y; t[2 * kTileStride] = self.z; t[3 * kTileStride] = self.w;
+        t[0] = self[p].x; t[kTileStride] = self[p].y; t[2 * kTileStride] = self[p].z; t[3 * kTileStride] = self[p].w;
     }
     __syncwarp();
 }
@@ -375,17 +390,19 @@ __device__ __forceinline__ void gather16_mid_task(float *__restrict__ feat, uint
 
 // ---- gather, width 1, tiles: one lane per vertex -------------------------------------------
 __device__ __noinline__ void gather1_tile(float *__restrict__ T, uint32_t *__restrict__ vid,
-                                             const uint32_t *__restrict__ order, uint32_t pos0, int count,
-                                             const uint32_t *__restrict__ row_ptr,
+                                             const uint4 *__restrict__ vrec, uint32_t pos0, int count,
                                              const uint32_t *__restrict__ col,
-                                             const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
+                                             const uint32_t *__restrict__ NWv,
                                              const float *__restrict__ x, uint32_t v_begin, float scale,
                                              int lane) {
     float agg = 0.0f, xs = 0.0f, fd = 0.0f, fw = 0.0f, fnw = 0.0f;
     if (lane < count) {
-        const uint32_t ul = __ldg(order + pos0 + lane);
-        uint32_t e = __ldg(row_ptr + ul);
-        const uint32_t end = __ldg(row_ptr + ul + 1);
+        const uint4 rec = __ldg(vrec + pos0 + lane);     // {id, row begin, row end, W}
+        const uint32_t ul = rec.x;
+        uint32_t e = rec.y;
+        const uint32_t end = rec.z;
+        const uint32_t nw = __ldg(NWv + ul);
+        xs = __ldg(x + v_begin + ul);
         fd = __uint2float_rn(end - e);
         uint32_t id[8], nid[8];
 #pragma unroll
@@ -402,9 +419,8 @@ __device__ __noinline__ void gather1_tile(float *__restrict__ T, uint32_t *__res
 #pragma unroll
             for (int t = 0; t < 8; ++t) id[t] = nid[t];
         }
-        xs = __ldg(x + v_begin + ul);
-        fw = __fdiv_rn(__uint2float_rn(__ldg(Wv + ul)), scale);
-        fnw = __fdiv_rn(__uint2float_rn(__ldg(NWv + ul)), scale);
+        fw = __fdiv_rn(__uint2float_rn(rec.w), scale);
+        fnw = __fdiv_rn(__uint2float_rn(nw), scale);
         vid[lane] = v_begin + ul;
     }
     T[0 * kTileStride + lane] = agg;    // [agg | x | D | W/s | NW/s], :33-40 with w = 1
@@ -602,7 +618,8 @@ template <int STAGE, bool EXACT>
 __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
              const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
-             const uint32_t *__restrict__ order, const Schedule sc, float *__restrict__ feat,
+             const uint32_t *__restrict__ order, const uint4 *__restrict__ vrec, const Schedule sc,
+             float *__restrict__ feat,
              uint32_t *__restrict__ sync, const float *__restrict__ in, float *__restrict__ out,
              const float *__restrict__ params, uint32_t v_begin, float scale) {
     constexpr StageDims D = stage_dims(STAGE);
@@ -671,9 +688,9 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
                 const uint32_t pos0 = n_pre + (g - n_front) * kTileVerts;
                 const int count = (int)min((uint32_t)kTileVerts, sc.n_local - pos0);
                 if constexpr (STAGE == 0)
-                    gather1_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv, in, v_begin, scale, lane);
+                    gather1_tile(T, vid, vrec, pos0, count, col, NWv, in, v_begin, scale, lane);
                 else
-                    gather16_tile(T, vid, order, pos0, count, row_ptr, col, Wv, NWv,
+                    gather16_tile(T, vid, vrec, pos0, count, col, NWv,
                                   reinterpret_cast<const float4 *>(in), v_begin, scale, lane);
                 tile_dense_and_store<STAGE, EXACT>(T, vid, count, P, out, v_begin, lane);
             }
@@ -720,12 +737,15 @@ __global__ void degree_hist_kernel(const uint32_t *__restrict__ row_ptr, uint32_
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-__global__ void degree_scatter_kernel(const uint32_t *__restrict__ row_ptr, uint32_t n_local,
+__global__ void degree_scatter_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ Wv,
+                                      uint32_t n_local,
                                       uint32_t *__restrict__ cursor /* kNumDegBins: start of each bin */,
-                                      uint32_t *__restrict__ order) {
+                                      uint32_t *__restrict__ order, uint4 *__restrict__ vrec) {
     for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_local; u += gridDim.x * blockDim.x) {
-        const uint32_t pos = atomicAdd(&cursor[degree_bin(row_ptr[u + 1] - row_ptr[u])], 1u);
+        const uint32_t beg = row_ptr[u], end = row_ptr[u + 1];
+        const uint32_t pos = atomicAdd(&cursor[degree_bin(end - beg)], 1u);
         order[pos] = u;
+        vrec[pos] = make_uint4(u, beg, end, Wv[u]);      // everything a tile needs about the vertex, 16 B
     }
 }
 

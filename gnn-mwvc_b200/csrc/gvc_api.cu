@@ -267,7 +267,7 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     sc_launch.n_ring_ctas = std::min<unsigned>(grid, (unsigned)c->num_sms);   // one ring CTA per SM at most
     const size_t smem = stage_smem_bytes<STAGE>();
     // task counter + per-feature-tile completion counters start at zero
-    GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (1 + (size_t)sc.n_feat_tiles) * sizeof(uint32_t), c->stream));
+    GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (3 + (size_t)sc.n_feat_tiles) * sizeof(uint32_t), c->stream));
     if (mode == GVC_MODE_EXACT) {
         stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
             c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
@@ -324,7 +324,7 @@ int build_schedule(gvc_ctx *c) {
     sc.n_tiles = (nl - n_pre + kTileVerts - 1) / kTileVerts;
     sc.n_feat_tiles = (n_pre + kTileVerts - 1) / kTileVerts;
     if ((rc = c->d_feat.reserve((size_t)n_pre * 32))) return rc;
-    if ((rc = c->d_sync.reserve(1 + (size_t)sc.n_feat_tiles))) return rc;
+    if ((rc = c->d_sync.reserve(3 + (size_t)sc.n_feat_tiles))) return rc;
     GVC_CUDA(cudaMemcpyAsync(c->d_bins.p, start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
     degree_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, c->Wv, nl, c->d_bins.p, c->d_order.p, c->d_vrec.p);
     GVC_CUDA(cudaGetLastError());

@@ -64,12 +64,16 @@ constexpr int kTileRows = 32;             // widest activation
 constexpr int kTileFloats = kTileRows * kTileStride;
 constexpr int kWarpSmemFloats = kTileFloats + 32;   // tile + vid[32]
 
+#ifndef GVC_HEAVY_WARPS
+#define GVC_HEAVY_WARPS 4
+#endif
 #ifndef GVC_RING_MIN_DEG
 #define GVC_RING_MIN_DEG 2048
 #endif
 #ifndef GVC_MID_MIN_DEG
 #define GVC_MID_MIN_DEG 64
 #endif
+constexpr int kHeavyWarps = GVC_HEAVY_WARPS;    // warps per CTA that draw tasks from the heavy end of the list
 constexpr uint32_t kRingMinDeg = GVC_RING_MIN_DEG;    // >= : ring task (whole CTA)
 constexpr uint32_t kCoopMinDeg = GVC_MID_MIN_DEG;      // >= : coop task (one warp per vertex), below: 32-vertex tiles
 constexpr int kNumDegBins = 132;
@@ -613,7 +617,7 @@ __device__ __forceinline__ void publish_feature(uint32_t *__restrict__ ready, ui
 // STAGE 0: in = x [n_global],      out = h rows [n_global x 16]
 // STAGE 1: in = h [n_global x 16], out = h rows [n_global x 16]
 // STAGE 2: in = h [n_global x 16], out = scores [n_local]
-// sync[0] = task counter, sync[1 + t] = finished feature vectors of feature tile t; zeroed before launch.
+// sync[0..2] = task counters, sync[3 + t] = finished feature vectors of feature tile t; zeroed before launch.
 template <int STAGE, bool EXACT>
 __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
@@ -635,7 +639,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *T = warp_mem + warp * kWarpSmemFloats;
     uint32_t *vid = reinterpret_cast<uint32_t *>(T + kTileFloats);
-    uint32_t *ready = sync + 1;
+    uint32_t *ready = sync + 3;
 
     // ---- ring tasks (width 16 only): the whole CTA, largest vertices first --------------------
     // With w = 1 the chain costs the same 4 cycles per neighbour whoever feeds it and one warp
@@ -663,14 +667,24 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     const uint32_t n_tiles = (sc.n_local - n_pre + kTileVerts - 1) / kTileVerts;
     const uint32_t n_heavy = n_front + n_tiles;             // dealt alternately from both ends
     const uint32_t n_tasks = n_heavy + (n_pre + kTileVerts - 1) / kTileVerts;
+    // Two-ended task list: [front tasks, heaviest first | tiles, heavier to lighter].  Warps with a
+    // "heavy" role draw from the front, the others from the back, so that every SM always has warps
+    // stalled on gathers AND warps running dense tiles (with a single alternating counter all warps
+    // end up holding long gather tasks at the same time and the FMA pipes idle).  sync[0] counts all
+    // claims, sync[1] the front claims, sync[2] the back claims: front ids 0..F-1 and back ids
+    // n-1..n-B can never meet because F + B <= n.
+    const bool heavy_role = warp < kHeavyWarps;
 #pragma unroll 1
     for (;;) {
-        uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(sync, 1u);
+        uint32_t k = 0, g = 0;
+        if (lane == 0) {
+            k = atomicAdd(sync, 1u);
+            if (k < n_heavy) g = heavy_role ? atomicAdd(sync + 1, 1u) : n_heavy - 1 - atomicAdd(sync + 2, 1u);
+        }
         k = __shfl_sync(0xffffffffu, k, 0);
+        g = __shfl_sync(0xffffffffu, g, 0);
         if (k >= n_tasks) break;
         if (k < n_heavy) {
-            const uint32_t g = (k & 1u) ? n_heavy - 1 - (k >> 1) : (k >> 1);
             if (g < n_front) {
                 if constexpr (STAGE == 0) {
                     const uint32_t ul = __ldg(order + g);

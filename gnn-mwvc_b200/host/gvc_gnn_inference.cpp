@@ -14,6 +14,7 @@
 // No OpenBLAS, no CPU arithmetic: a missing GPU is a fatal error.
 #include "gnn_inference.hpp"
 
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <random>
@@ -64,6 +65,24 @@ void extract_csr(const reduction_graph<Tn, Tw> &g, csr_scratch &s) {
         s.nw[u] = g.NW(u);
     }
 }
+
+// GVC_PROFILE=1: per-call and cumulative timing of predict() on stderr (CSR extraction on the
+// host, graph upload + schedule, forward incl. the copies of x and the scores).
+struct predict_profile {
+    bool on = std::getenv("GVC_PROFILE") != nullptr;
+    int calls = 0;
+    double extract = 0, upload = 0, forward = 0;
+    ~predict_profile() {
+        if (on)
+            std::fprintf(stderr, "gvc profile: %d predict calls, extract %.3f s, upload %.3f s, forward %.3f s, total %.3f s\n",
+                         calls, extract, upload, forward, extract + upload + forward);
+    }
+};
+predict_profile &profile() {
+    static predict_profile p;
+    return p;
+}
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // Fingerprint of a model's layers, to know when the device copy is stale.
 struct model_key {
@@ -200,12 +219,21 @@ void model::predict(const matrix &in, matrix &out, const reduction_graph<Tn, Tw>
     for (auto &c : layers)
         if (auto *gl = std::get_if<graph_layer>(&c)) { scale = gl->WEIGHT_SCALE; break; }
 
+    predict_profile &pf = profile();
+    const double t0 = now_s();
     csr_scratch &s = scratch();
     extract_csr(g, s);
+    const double t1 = now_s();
     int rc = gvc_graph_upload(ctx, n, s.row_ptr.data(), s.col.data(), s.w.data(), s.nw.data());
     if (rc != 0) gvc_host::die("gvc_graph_upload", rc);
+    const double t2 = now_s();
     rc = gvc_forward(ctx, cdata(in), scale, mdata(out), gvc_host::mode());
     if (rc != 0) gvc_host::die("gvc_forward", rc);
+    const double t3 = now_s();
+    pf.calls++; pf.extract += t1 - t0; pf.upload += t2 - t1; pf.forward += t3 - t2;
+    if (pf.on)
+        std::fprintf(stderr, "gvc profile: predict n=%u nnz=%zu extract %.2f ms upload %.2f ms forward %.2f ms\n", n,
+                     s.col.size(), 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2));
 }
 
 // ---- text format (src/gnn_inference.cpp:92-139) --------------------------------

@@ -333,6 +333,23 @@ def run_ours(args):
                     b.record(stream)
                     b.synchronize()
                     stage_ms[st].append(a.elapsed_time(b))
+        # ---- the other arithmetic mode, same graph, for the record (N = 1) ----------------------------
+        other = None
+        if world == 1:
+            omode = pkg.MODE_FAST if mode == pkg.MODE_EXACT else pkg.MODE_EXACT
+            for _ in range(3):
+                ctx.forward_device(x_full, weight_scale, scores, omode)
+            oms = []
+            for i in range(max(5, min(args.steps, 20))):
+                flush.fill_(i & 0xFF)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                ctx.forward_device(x_full, weight_scale, scores, omode)
+                b.record(stream)
+                b.synchronize()
+                oms.append(a.elapsed_time(b))
+            other = {"mode": "fast" if omode == pkg.MODE_FAST else "exact", "ms_per_step": float(np.mean(oms)),
+                     "value": max(e_total, 1) / (float(np.mean(oms)) * 1e-3), "unit": UNIT}
         torch.cuda.synchronize()
 
     # max over ranks of the per-rank timed total
@@ -413,7 +430,7 @@ def run_ours(args):
                        "sharding": "single GPU" if world == 1 else f"{world} equal vertex ranges of the cyclically relabelled graph (v -> shard v % {world}), NCCL all-gather of 16-float rows after stages 0 and 1",
                        "graph_generation_s": round(gen_s, 2)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "phase_ms": phase_ms,
+            "roofline": roof, "cpu_baseline": cpu, "phase_ms": phase_ms, "other_mode": other,
             "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
         }
         print(json.dumps(line), flush=True)

@@ -498,7 +498,7 @@ __device__ __forceinline__ float chain_add16(const float *__restrict__ S, int cn
 // to warp through shared memory, the hand-over for batch b is named barrier 1 + b % 8
 // (arrive by the warp that summed b-1, sync by the warp that sums b).  All 8 warps call
 // this; the caller reads the 16 sums from ring_acc after a __syncthreads().
-__device__ __noinline__ void ring_gather16(float *__restrict__ S, float *__restrict__ ring_acc,
+__device__ __noinline__ void ring_gather16_exact(float *__restrict__ S, float *__restrict__ ring_acc,
                                               const uint32_t *__restrict__ col,
                                               const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
                                               int warp, int lane) {
@@ -523,6 +523,34 @@ __device__ __noinline__ void ring_gather16(float *__restrict__ S, float *__restr
         if (lane < 16) ring_acc[lane] = acc;
         if (b + 1 < nb) named_bar_arrive(1 + (int)((b + 1) % kWarpsPerCta), 64);
     }
+}
+
+// Fast mode does not owe the reference its summation order: every warp sums its own batches in
+// registers (no staging, no hand-over), the 8 sub-warps and then the 8 warps are combined in a
+// fixed order, so the result is deterministic but not the sequential chain.  ring_acc gets the
+// 16 sums after the caller's __syncthreads(); `part` is kWarpsPerCta x 16 floats of shared memory.
+__device__ __noinline__ void ring_gather16_fast(float *__restrict__ part, const uint32_t *__restrict__ col,
+                                                const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
+                                                int warp, int lane) {
+    const uint32_t nb = (end - beg + 63) / 64;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r[8];
+    uint32_t b = warp;
+    BatchIds ids = coop_load_ids(col, beg + 64 * b, end, lane);
+#pragma unroll 1
+    for (; b < nb; b += kWarpsPerCta) {
+        const uint32_t e0 = beg + 64 * b;
+        coop_load_rows16(r, ids, in4, e0, end, lane);          // rows past `end` come back as zeros
+        ids = coop_load_ids(col, e0 + 64 * kWarpsPerCta, end, lane);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { acc.x += r[w].x; acc.y += r[w].y; acc.z += r[w].z; acc.w += r[w].w; }
+    }
+#pragma unroll
+    for (int m = 4; m < 32; m <<= 1) {                         // the 8 sub-warps hold the same 4 columns
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, m); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, m);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, m); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, m);
+    }
+    if (lane < 4) *reinterpret_cast<float4 *>(part + warp * 16 + 4 * lane) = acc;
 }
 
 // ---- width 1 ---------------------------------------------------------------------------------------
@@ -574,6 +602,23 @@ __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 float
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[t] = vn[t];
     }
+    return acc;
+}
+
+// fast mode: every lane sums its own elements, one shuffle reduction at the end
+__device__ __noinline__ float coop_gather1_fast(const uint32_t *__restrict__ col, const float *__restrict__ x,
+                                                uint32_t beg, uint32_t end, int lane) {
+    float acc = 0.0f;
+#pragma unroll 1
+    for (uint32_t e0 = beg; e0 < end; e0 += 256) {
+        uint32_t id[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < end) ? ld_id(col + e) : 0u; }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; acc += (e < end) ? __ldg(x + id[t]) : 0.0f; }
+    }
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
     return acc;
 }
 
@@ -649,8 +694,20 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
         for (uint32_t g = blockIdx.x; blockIdx.x < sc.n_ring_ctas && g < sc.n_ring; g += sc.n_ring_ctas) {
             const uint32_t ul = __ldg(order + g);
             const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-            ring_gather16(T, ring_acc, col, reinterpret_cast<const float4 *>(in), beg, end, warp, lane);
-            __syncthreads();
+            if constexpr (EXACT) {
+                ring_gather16_exact(T, ring_acc, col, reinterpret_cast<const float4 *>(in), beg, end, warp, lane);
+                __syncthreads();
+            } else {
+                float *part = warp_mem;                    // warp 0's tile buffer: free during the ring phase
+                ring_gather16_fast(part, col, reinterpret_cast<const float4 *>(in), beg, end, warp, lane);
+                __syncthreads();
+                if (threadIdx.x < 16) {
+                    float sum = 0.0f;
+                    for (int w = 0; w < kWarpsPerCta; ++w) sum += part[w * 16 + threadIdx.x];
+                    ring_acc[threadIdx.x] = sum;
+                }
+                __syncthreads();
+            }
             if (warp == 0) {
                 put_features16(feat, g, ring_acc[lane & 15], in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
                 publish_feature(ready, g, lane);
@@ -689,7 +746,8 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
                 if constexpr (STAGE == 0) {
                     const uint32_t ul = __ldg(order + g);
                     const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-                    const float acc = coop_gather1(T, col, in, beg, end, lane);
+                    const float acc = EXACT ? coop_gather1(T, col, in, beg, end, lane)
+                                            : coop_gather1_fast(col, in, beg, end, lane);
                     put_features1(feat, g, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
                     publish_feature(ready, g, lane);
                 } else {

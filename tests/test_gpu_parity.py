@@ -88,6 +88,32 @@ def test_forward_vs_oracle(ctx, oracle, oracle_model, maker):
     assert np.array_equal((fast > 0.5)[clear], (want > 0.5)[clear])
 
 
+def test_degree_ladder_hits_every_gather_path(ctx, oracle, oracle_model):
+    """Degrees around the class thresholds of the gather schedule (64: 4-lanes-per-vertex mid tasks,
+    2048: the CTA-wide ring with its warp-to-warp hand-over) and a giant of ~70 000 neighbours whose
+    ring runs many rounds on all 8 warps; shuffled adjacency so the order matters.  Bit-exact."""
+    rng = np.random.default_rng(11)
+    n = 90_000
+    want_deg = {0: 70_001, 1: 2047, 2: 2048, 3: 2049, 4: 4097, 5: 63, 6: 64, 7: 65, 8: 511, 9: 129, 10: 1, 11: 8191}
+    eu, ev = [], []
+    for u, d in want_deg.items():
+        nb = rng.choice(np.arange(100, n), size=d, replace=False)
+        eu.append(np.full(d, u)); ev.append(nb)
+    extra = rng.integers(100, n, size=(200_000, 2))
+    eu.append(extra[:, 0]); ev.append(extra[:, 1])
+    eu, ev = torch.from_numpy(np.concatenate(eu)), torch.from_numpy(np.concatenate(ev))
+    a, b = graphs._canonical_edges(eu, ev, n)
+    g = graphs.graph_from_edges(n, a, b, graphs.random_weights(n, 12), name="ladder")
+    rp, col, W, NW, x, s = inputs_of(g)
+    col = col.copy()
+    for u in want_deg:                                   # the big lists in a non-ascending order
+        rng.shuffle(col[int(rp[u]):int(rp[u + 1])])
+    want = oracle.predict(oracle_model, rp, col, W, NW, x, s)[:, 0]
+    ctx.graph_upload(rp, col, W, NW)
+    assert_bit_equal(ctx.forward(x, s, pkg.MODE_EXACT), want, "ladder")
+    assert_rel_close(ctx.forward(x, s, pkg.MODE_FAST), want, FAST_RTOL, "ladder fast")
+
+
 def test_stage_outputs_vs_oracle(ctx, oracle, model_layers):
     g = graphs.rmat_graph(12, 16, seed=41, n_limit=4001)
     rp, col, W, NW, x, s = inputs_of(g)

@@ -4,9 +4,9 @@ max=${1:-8}
 for n in 1 2 4 8; do
   [ $n -gt $max ] && break
   if [ $n -eq 1 ]; then
-    python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
+    python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --mode ${MODE:-exact} > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
   else
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 10 --warmup 3 --mode ${MODE:-exact} > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
   fi
   echo "n=$n rc=$?"
   python - <<PY

@@ -62,7 +62,7 @@ def build_dropin(force: bool = False) -> Path | None:
         cmd = ["/usr/bin/g++", "-std=c++17", "-O3", "-march=x86-64-v3", "-DNDEBUG",
                "-I", str(REF / "include"), "-I", str(ROOT / "include"), "-I", str(PKG / "host"), "-o", str(out),
                str(REF / "src" / "GNN_VC.cpp"), str(srcs[0]), str(srcs[1]),
-               "-L", str(PKG), "-lgvc", "-Wl,-rpath,$ORIGIN/../..", "-Wl,-rpath," + str(PKG)]
+               "-L", str(PKG), "-lgvc", "-pthread", "-Wl,-rpath,$ORIGIN/../..", "-Wl,-rpath," + str(PKG)]
         subprocess.check_call(cmd)
     return out
 

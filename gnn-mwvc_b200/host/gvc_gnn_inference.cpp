@@ -18,7 +18,9 @@
 #include <cmath>
 #include <cstdint>
 #include <random>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gvc.h"
@@ -52,18 +54,33 @@ void extract_csr(const reduction_graph<Tn, Tw> &g, csr_scratch &s) {
     s.row_ptr.resize((size_t)n + 1);
     s.w.resize(n);
     s.nw.resize(n);
-    uint64_t total = 0;
-    for (Tn u = 0; u < n; ++u) {
-        s.row_ptr[u] = total;
-        total += (uint64_t)(g.end(u) - g.begin(u));
-    }
-    s.row_ptr[n] = total;
-    s.col.resize(total);
-    for (Tn u = 0; u < n; ++u) {
-        std::copy(g.begin(u), g.end(u), s.col.begin() + s.row_ptr[u]);
-        s.w[u] = g.W(u);
-        s.nw[u] = g.NW(u);
-    }
+    // begin(u)/end(u)/W(u)/NW(u) only read the graph, so vertex ranges can be walked by several
+    // threads (never D(u) / operator[], which write a cursor)
+    const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned nt = n < (1u << 16) ? 1u : std::min(16u, hw ? hw : 1u);
+    auto for_ranges = [&](auto &&fn) {
+        if (nt == 1) { fn((Tn)0, n); return; }
+        std::vector<std::thread> th;
+        const Tn step = (n + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; ++t) {
+            const Tn a = std::min<uint64_t>((uint64_t)t * step, n), b = std::min<uint64_t>((uint64_t)(t + 1) * step, n);
+            if (a < b) th.emplace_back([&fn, a, b] { fn(a, b); });
+        }
+        for (auto &x : th) x.join();
+    };
+    for_ranges([&](Tn a, Tn b) {
+        for (Tn u = a; u < b; ++u) {
+            s.row_ptr[u + 1] = (uint64_t)(g.end(u) - g.begin(u));     // degree, turned into an offset below
+            s.w[u] = g.W(u);
+            s.nw[u] = g.NW(u);
+        }
+    });
+    s.row_ptr[0] = 0;
+    for (Tn u = 0; u < n; ++u) s.row_ptr[u + 1] += s.row_ptr[u];
+    s.col.resize(s.row_ptr[n]);
+    for_ranges([&](Tn a, Tn b) {
+        for (Tn u = a; u < b; ++u) std::copy(g.begin(u), g.end(u), s.col.begin() + s.row_ptr[u]);
+    });
 }
 
 // GVC_PROFILE=1: per-call and cumulative timing of predict() on stderr (CSR extraction on the

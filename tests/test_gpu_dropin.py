@@ -41,3 +41,26 @@ def test_er10k_cover_identical_to_reference(er10k, tmp_path, mode):
         assert hashlib.md5(out.read_bytes()).hexdigest() == gold["result_md5"]
     else:   # fast mode promises 1e-4 on scores; on this graph the cover still comes out identical
         assert int(fields[1]) == gold["cost"]
+
+
+def test_config5_full_run_on_shrinking_graphs(tmp_path):
+    """BASELINE config 5 in small: a whole GNN_VC run (ER, 60 000 vertices / 300 000 edges, time = 0) calls
+    predict() ~8 times on a shrinking, relabelled graph.  The drop-in binary on the B200 (exact mode) must
+    write the same cover as the CPU reference (one OpenBLAS thread, the order exact mode reproduces)."""
+    from oracle import pyoracle as po
+    if not BIN.exists() or not po.REF_BIN.exists():
+        pytest.skip("needs oracle/_ref and the drop-in binary (built where /root/reference exists)")
+    g = graphs.er_graph(60_000, 300_000, seed=5)
+    gp = tmp_path / "er60k.graph"
+    graphs.write_metis(g, gp)
+    outs = {}
+    for name, exe, env in (("ref", po.REF_BIN, {"OPENBLAS_CORETYPE": "Prescott", "OPENBLAS_NUM_THREADS": "1"}),
+                           ("gpu", BIN, {"GVC_MODE": "exact", "GVC_PROFILE": "1"})):
+        out = tmp_path / f"{name}.out"
+        r = subprocess.run([str(exe), str(gp), str(out), "0", "-1", "0"], capture_output=True, text=True,
+                           env=dict(os.environ, **env), timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs[name] = (r.stdout.strip().split(",")[1], hashlib.md5(out.read_bytes()).hexdigest(), r.stderr)
+    assert outs["gpu"][0] == outs["ref"][0], "cover cost differs"
+    assert outs["gpu"][1] == outs["ref"][1], "cover differs"
+    assert "predict calls" in outs["gpu"][2]          # the forward really went through libgvc

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -533,7 +534,7 @@ int gvc_graph_upload_shard(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
     if (nnz >= (1ull << 32)) return fail(GVC_ERR_UNSUPPORTED, "shard has %llu adjacency entries; 2^32 is the limit", (unsigned long long)nnz);
     if (nnz && !col) return fail(GVC_ERR_ARG, "null col");
     if ((rc = c->own_row_ptr.reserve((size_t)nl + 1))) return rc;
-    if ((rc = c->own_col.reserve(nnz))) return rc;
+    if ((rc = c->own_col.reserve(nnz + 4))) return rc;      // readable up to the next multiple of four ids
     if ((rc = c->own_W.reserve(nl))) return rc;
     if ((rc = c->own_NW.reserve(nl))) return rc;
     // narrow the 64-bit offsets to the 32-bit layout the kernels read (pinned staging)
@@ -566,7 +567,24 @@ int gvc_graph_adopt_device(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
     if (v_begin > v_end || v_end > n_global) return fail(GVC_ERR_ARG, "bad shard [%u,%u) of %u", v_begin, v_end, n_global);
     if (v_end > v_begin && (!d_row_ptr || !d_W || !d_NW)) return fail(GVC_ERR_ARG, "null graph arrays");
     if ((rc = use_device(c))) return rc;
-    return set_graph_views(c, n_global, v_begin, v_end, d_row_ptr, d_col, d_W, d_NW, 0);
+    // The gather reads neighbour ids as aligned groups of four (gvc_kernels.cuh ld_id4): the id
+    // array must start on a 16-byte boundary and be readable up to the next multiple of four
+    // entries.  A caller's buffer that does not guarantee that (a slice of a bigger array, a
+    // length that is not a multiple of four) is copied once into a buffer that does.
+    const uint32_t nl = v_end - v_begin;
+    uint32_t nnz = 0;
+    if (nl) {
+        GVC_CUDA(cudaMemcpyAsync(&nnz, d_row_ptr + nl, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        GVC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (nnz && !d_col) return fail(GVC_ERR_ARG, "null col");
+    const uint32_t *col = d_col;
+    if (nnz && ((reinterpret_cast<uintptr_t>(d_col) & 15u) || (nnz & 3u))) {
+        if ((rc = c->own_col.reserve((size_t)nnz + 4))) return rc;
+        GVC_CUDA(cudaMemcpyAsync(c->own_col.p, d_col, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, c->stream));
+        col = c->own_col.p;
+    }
+    return set_graph_views(c, n_global, v_begin, v_end, d_row_ptr, col, d_W, d_NW, nnz);
 }
 
 int gvc_graph_set_tail(gvc_ctx *c, int has_tail, uint32_t local_index) {

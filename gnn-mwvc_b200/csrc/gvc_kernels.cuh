@@ -239,6 +239,10 @@ __device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const u
     const float *Wa = P, *ba = Wa + D.Ka * D.Na;
     const float *Wb = ba + D.Na, *bb = Wb + D.Kb * D.Nb;
     const float *Wc = bb + D.Nb, *bc = Wc + D.Kc * D.Nc;
+#ifdef GVC_DEBUG_SKIP_DENSE      // diagnostic build only: how long does the gather take on its own?
+    if (lane < count) out[(size_t)(vid[lane] - (STAGE < 2 ? 0u : v_begin)) * (STAGE < 2 ? 16 : 1)] = T[lane];
+    return;
+#endif
     tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane);
     tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane);
     if constexpr (STAGE < 2) {
@@ -260,52 +264,59 @@ __device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const u
 
 // ---- gather, width 16: 4 lanes per vertex ------------------------------------------------------
 // One sub-warp (lanes 4s..4s+3, lane q holds floats 4q..4q+3 of every row) sums the rows of
-// one vertex in adjacency order.  Chunks of kChunk neighbours; the ids of chunks k+1 and k+2 and
+// one vertex in adjacency order.
 // the rows of chunk k+1 are in flight while chunk k is added (in-order issue: a load is never
 // consumed in the phase that issued it).  Two register sets alternate.
-#ifndef GVC_GATHER_CHUNK
-#define GVC_GATHER_CHUNK 4
-#endif
-constexpr int kChunk = GVC_GATHER_CHUNK;
-
-__device__ __forceinline__ void load_ids(uint32_t (&id)[kChunk], const uint32_t *__restrict__ col, uint32_t e,
-                                         uint32_t end) {
-#pragma unroll
-    for (int t = 0; t < kChunk; ++t) id[t] = (e + t < end) ? ld_id(col + e + t) : 0u;
+// Neighbour ids are fetched as aligned groups of four (one 128-bit load per sub-warp instead of
+// four 32-bit ones: the id loads were half of the kernel's L1 wavefronts).  Group g holds
+// col[4g .. 4g+3]; entries before the row's begin or at/after its end are masked, so a row may
+// start and stop anywhere.  `col` is 16-byte aligned and readable up to the next multiple of 4
+// entries (the host side guarantees both).
+__device__ __forceinline__ uint4 ld_id4(const uint32_t *__restrict__ col, uint32_t g) {
+    return __ldcs(reinterpret_cast<const uint4 *>(col) + g);
 }
-__device__ __forceinline__ void load_rows(float4 (&r)[kChunk], const uint32_t (&id)[kChunk],
-                                          const float4 *__restrict__ in4, int q, uint32_t e, uint32_t end) {
-#pragma unroll
-    for (int t = 0; t < kChunk; ++t)
-        if (e + t < end) r[t] = ldg_row4(in4 + (size_t)id[t] * 4 + q);
+__device__ __forceinline__ void load_rows4(float4 (&r)[4], const uint4 id, const float4 *__restrict__ in4, int q,
+                                           uint32_t g, uint32_t beg, uint32_t end) {
+    const uint32_t e = 4 * g;
+    if (e + 0 >= beg && e + 0 < end) r[0] = ldg_row4(in4 + (size_t)id.x * 4 + q);
+    if (e + 1 >= beg && e + 1 < end) r[1] = ldg_row4(in4 + (size_t)id.y * 4 + q);
+    if (e + 2 >= beg && e + 2 < end) r[2] = ldg_row4(in4 + (size_t)id.z * 4 + q);
+    if (e + 3 >= beg && e + 3 < end) r[3] = ldg_row4(in4 + (size_t)id.w * 4 + q);
 }
-__device__ __forceinline__ void add_rows(float4 &acc, const float4 (&r)[kChunk], uint32_t e, uint32_t end) {
+__device__ __forceinline__ void add_rows4(float4 &acc, const float4 (&r)[4], uint32_t g, uint32_t beg,
+                                          uint32_t end) {
+    const uint32_t e = 4 * g;
 #pragma unroll
-    for (int t = 0; t < kChunk; ++t)
-        if (e + t < end) {
+    for (int t = 0; t < 4; ++t)
+        if (e + t >= beg && e + t < end) {
             acc.x = __fadd_rn(acc.x, r[t].x); acc.y = __fadd_rn(acc.y, r[t].y);
             acc.z = __fadd_rn(acc.z, r[t].z); acc.w = __fadd_rn(acc.w, r[t].w);
         }
 }
 
+// Groups k+1 and k+2's ids and group k+1's rows are in flight while group k is added (in-order
+// issue: a load is never consumed in the phase that issued it).  Two register sets alternate.
 __device__ __forceinline__ float4 gather16_vertex(const uint32_t *__restrict__ col,
                                                   const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
                                                   int q) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (beg >= end) return acc;
-    uint32_t idA[kChunk], idB[kChunk];
-    float4 rA[kChunk], rB[kChunk];
-    load_ids(idA, col, beg, end);
-    load_ids(idB, col, beg + kChunk, end);
-    load_rows(rA, idA, in4, q, beg, end);
-    for (uint32_t e = beg; e < end; e += 2 * kChunk) {
-        load_rows(rB, idB, in4, q, e + kChunk, end);
-        load_ids(idA, col, e + 2 * kChunk, end);
-        add_rows(acc, rA, e, end);
-        if (e + kChunk >= end) break;
-        load_rows(rA, idA, in4, q, e + 2 * kChunk, end);
-        load_ids(idB, col, e + 3 * kChunk, end);
-        add_rows(acc, rB, e + kChunk, end);
+    const uint32_t gend = (end + 3) >> 2;
+    uint32_t g = beg >> 2;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    uint4 idA = ld_id4(col, g);
+    uint4 idB = (g + 1 < gend) ? ld_id4(col, g + 1) : zero;
+    float4 rA[4], rB[4];
+    load_rows4(rA, idA, in4, q, g, beg, end);
+    for (;; g += 2) {
+        if (g + 1 < gend) load_rows4(rB, idB, in4, q, g + 1, beg, end);
+        idA = (g + 2 < gend) ? ld_id4(col, g + 2) : zero;
+        add_rows4(acc, rA, g, beg, end);
+        if (g + 1 >= gend) break;
+        if (g + 2 < gend) load_rows4(rA, idA, in4, q, g + 2, beg, end);
+        idB = (g + 3 < gend) ? ld_id4(col, g + 3) : zero;
+        add_rows4(acc, rB, g + 1, beg, end);
+        if (g + 2 >= gend) break;
     }
     return acc;
 }
@@ -408,20 +419,29 @@ __device__ __noinline__ void gather1_tile(float *__restrict__ T, uint32_t *__res
         const uint32_t nw = __ldg(NWv + ul);
         xs = __ldg(x + v_begin + ul);
         fd = __uint2float_rn(end - e);
-        uint32_t id[8], nid[8];
+        // ids as aligned groups of four (see ld_id4), two groups per trip, next trip's ids ahead
+        if (e < end) {
+            const uint32_t beg = e, gend = (end + 3) >> 2;
+            uint32_t g = beg >> 2;
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            uint4 i0 = ld_id4(col, g), i1 = (g + 1 < gend) ? ld_id4(col, g + 1) : zero;
+            for (; g < gend; g += 2) {
+                const uint4 n0 = (g + 2 < gend) ? ld_id4(col, g + 2) : zero;
+                const uint4 n1 = (g + 3 < gend) ? ld_id4(col, g + 3) : zero;
+                const uint32_t ids[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+                float a[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) id[t] = (e + t < end) ? ld_id(col + e + t) : 0u;
-        for (; e < end; e += 8) {
+                for (int t = 0; t < 8; ++t) {
+                    const uint32_t idx = 4 * g + t;
+                    a[t] = (idx >= beg && idx < end) ? __ldg(x + ids[t]) : 0.0f;
+                }
 #pragma unroll
-            for (int t = 0; t < 8; ++t) nid[t] = (e + 8 + t < end) ? ld_id(col + e + 8 + t) : 0u;
-            float a[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) a[t] = (e + t < end) ? __ldg(x + id[t]) : 0.0f;
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-                if (e + t < end) agg = __fadd_rn(agg, a[t]);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) id[t] = nid[t];
+                for (int t = 0; t < 8; ++t) {
+                    const uint32_t idx = 4 * g + t;
+                    if (idx >= beg && idx < end) agg = __fadd_rn(agg, a[t]);
+                }
+                i0 = n0; i1 = n1;
+            }
         }
         fw = __fdiv_rn(__uint2float_rn(rec.w), scale);
         fnw = __fdiv_rn(__uint2float_rn(nw), scale);

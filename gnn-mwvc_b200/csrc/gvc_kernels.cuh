@@ -64,6 +64,9 @@ constexpr int kTileRows = 32;             // widest activation
 constexpr int kTileFloats = kTileRows * kTileStride;
 constexpr int kWarpSmemFloats = kTileFloats + 32;   // tile + vid[32]
 
+#ifndef GVC_MID_SETS
+#define GVC_MID_SETS 2            // row sets of 4 in flight per vertex in the mid tasks (3 and 4 measured slower)
+#endif
 #ifndef GVC_HEAVY_WARPS
 #define GVC_HEAVY_WARPS 4
 #endif
@@ -321,6 +324,41 @@ __device__ __forceinline__ float4 gather16_vertex(const uint32_t *__restrict__ c
     return acc;
 }
 
+// Deeper pipeline for the mid tasks (no tile state to keep in registers there): S row sets and a
+// ring of DI id groups.  At the step that adds group G: the rows of G+1 .. G+S-1 and the ids of
+// G+S .. G+DI-1 are in flight; rows are requested with ids that were loaded DI-S+1 steps earlier,
+// so neither the id nor the row latency sits on the per-group critical path.
+template <int S, int DI>
+__device__ __forceinline__ float4 gather16_vertex_deep(const uint32_t *__restrict__ col,
+                                                       const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
+                                                       int q) {
+    static_assert(DI % S == 0 && DI >= S, "id ring must be a multiple of the row sets");
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beg >= end) return acc;
+    const uint32_t gend = (end + 3) >> 2;
+    const uint32_t g0 = beg >> 2;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    uint4 id[DI];
+    float4 r[S][4];
+#pragma unroll
+    for (int d = 0; d < DI; ++d) id[d] = (g0 + d < gend) ? ld_id4(col, g0 + d) : zero;
+#pragma unroll
+    for (int d = 0; d < S - 1; ++d)
+        if (g0 + d < gend) load_rows4(r[d], id[d], in4, q, g0 + d, beg, end);
+    for (uint32_t g = g0; g < gend; g += DI) {
+#pragma unroll
+        for (int j = 0; j < DI; ++j) {
+            const uint32_t G = g + j;
+            if (G < gend) {
+                if (G + S - 1 < gend) load_rows4(r[(j + S - 1) % S], id[(j + S - 1) % DI], in4, q, G + S - 1, beg, end);
+                add_rows4(acc, r[j % S], G, beg, end);
+                id[j] = (G + DI < gend) ? ld_id4(col, G + DI) : zero;
+            }
+        }
+    }
+    return acc;
+}
+
 // self features with the :38-40 quirk: D, W/s, NW/s overwrite self features 1..3
 __device__ __forceinline__ float4 self_features16(const float4 *__restrict__ in4, uint32_t ul, uint32_t deg,
                                                   const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
@@ -392,7 +430,7 @@ __device__ __forceinline__ void gather16_mid_task(float *__restrict__ feat, uint
         const uint32_t pos = pos0 + sv;
         const uint32_t ul = __ldg(order + pos);
         const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-        const float4 acc = gather16_vertex(col, in4, beg, end, q);
+        const float4 acc = gather16_vertex_deep<GVC_MID_SETS, 2 * GVC_MID_SETS>(col, in4, beg, end, q);
         const float4 self = self_features16(in4, ul, end - beg, Wv, NWv, v_begin, scale, q);
         float4 *f = reinterpret_cast<float4 *>(feat + (size_t)pos * 32);
         __stcg(f + q, acc);
@@ -610,6 +648,21 @@ __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 float
         const int cnt = (int)min(256u, end - e0);
         const float4 *s4 = reinterpret_cast<const float4 *>(S);
         int j = 0;
+        if (cnt == 256) {
+            // the next 16 values are loaded while the current 16 are added: the chain runs at the
+            // FADD latency (4 cycles per neighbour), not at shared-memory latency
+            float4 a = s4[0], b = s4[1], c = s4[2], d = s4[3];
+#pragma unroll 4
+            for (; j < 256; j += 16) {
+                const int n4 = (j + 16 < 256) ? (j + 16) / 4 : 0;
+                const float4 na = s4[n4], nb = s4[n4 + 1], nc = s4[n4 + 2], nd = s4[n4 + 3];
+                acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
+                acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y); acc = __fadd_rn(acc, b.z); acc = __fadd_rn(acc, b.w);
+                acc = __fadd_rn(acc, c.x); acc = __fadd_rn(acc, c.y); acc = __fadd_rn(acc, c.z); acc = __fadd_rn(acc, c.w);
+                acc = __fadd_rn(acc, d.x); acc = __fadd_rn(acc, d.y); acc = __fadd_rn(acc, d.z); acc = __fadd_rn(acc, d.w);
+                a = na; b = nb; c = nc; d = nd;
+            }
+        }
         for (; j + 16 <= cnt; j += 16) {
             const float4 a = s4[j / 4], b = s4[j / 4 + 1], c = s4[j / 4 + 2], d = s4[j / 4 + 3];
             acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);

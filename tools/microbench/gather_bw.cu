@@ -100,11 +100,19 @@ __global__ void gather_cpasync(const float4* __restrict__ table, const unsigned*
     if (acc.x == 12345.678f) out[sub * 4 + q] = acc;
 }
 
-int main() {
-    const size_t n = 1 << 20, m = 32u << 20;
+int main(int argc, char** argv) {
+    const size_t n = 1 << 20;
+    size_t m = 32u << 20;
     std::vector<unsigned> h(m);
     unsigned s = 12345;
     for (size_t i = 0; i < m; ++i) { s = s * 1664525u + 1013904223u; h[i] = (s >> 8) % n; }
+    if (argc > 1) {   // ids from a file (uint32): e.g. the col array of the R-MAT benchmark graph
+        FILE* f = fopen(argv[1], "rb");
+        if (!f) { printf("cannot open %s\n", argv[1]); return 1; }
+        m = fread(h.data(), 4, m, f) / 1024 * 1024;
+        fclose(f);
+        printf("ids from %s: %zu entries\n", argv[1], m);
+    }
     float4* table; unsigned* ids; float4* out;
     cudaMalloc(&table, n * 64); cudaMalloc(&ids, m * 4); cudaMalloc(&out, 64 << 20);
     cudaMemset(table, 0, n * 64);

@@ -261,7 +261,7 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     if (nl == 0) return 0;
     const Schedule &sc = c->sched;
     const uint32_t n_tasks = STAGE == 0 ? sc.n_ring + (nl - sc.n_ring + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
-                                        : (sc.n_coop + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
+                                        : (sc.n_mid + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
     const unsigned want = std::max<unsigned>(STAGE == 0 ? 0u : sc.n_ring, (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
     const unsigned grid = std::max(1u, std::min<unsigned>(kCtasPerSm * c->num_sms, want));
     Schedule sc_launch = sc;
@@ -314,14 +314,14 @@ int build_schedule(gvc_ctx *c) {
     uint32_t pos = 0, n_ring = 0, n_pre = 0;
     for (int b = kNumDegBins - 1; b >= 0; --b) {          // descending degree
         if (b == degree_bin(kRingMinDeg) - 1) n_ring = pos;
-        if (b == degree_bin(kCoopMinDeg) - 1) n_pre = pos;
+        if (b == degree_bin(kMidMinDeg) - 1) n_pre = pos;
         start[b] = pos;
         pos += hist[b];
     }
     Schedule &sc = c->sched;
     sc.n_local = nl;
     sc.n_ring = n_ring;
-    sc.n_coop = n_pre - n_ring;
+    sc.n_mid = n_pre - n_ring;
     sc.n_tiles = (nl - n_pre + kTileVerts - 1) / kTileVerts;
     sc.n_feat_tiles = (n_pre + kTileVerts - 1) / kTileVerts;
     if ((rc = c->d_feat.reserve((size_t)n_pre * 32))) return rc;

@@ -34,9 +34,10 @@
 //   tile    deg < 64      32 vertices per warp, 4 lanes per vertex (1 for w=1)
 // ring and mid tasks only produce the 32-float feature vector (side buffer,
 // 128 B per vertex); "feature tiles" later run the dense chain on 32 of them, so
-// no dense work is wasted on part-filled tiles.  The kernel is persistent: warps
-// draw tasks from an atomic counter, heavy and light tasks alternately, so that
-// bandwidth-bound gathers and FMA-bound dense tiles overlap on every SM.
+// no dense work is wasted on part-filled tiles.  The kernel is persistent: the
+// tasks form a two-ended list (heaviest gathers ... lightest tiles); half of the
+// warps of every CTA draw from the heavy end, half from the light end, so that
+// latency-bound gathers and FMA-bound dense tiles overlap on every SM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -78,17 +79,17 @@ constexpr int kWarpSmemFloats = kTileFloats + 32;   // tile + vid[32]
 #endif
 constexpr int kHeavyWarps = GVC_HEAVY_WARPS;    // warps per CTA that draw tasks from the heavy end of the list
 constexpr uint32_t kRingMinDeg = GVC_RING_MIN_DEG;    // >= : ring task (whole CTA)
-constexpr uint32_t kCoopMinDeg = GVC_MID_MIN_DEG;      // >= : coop task (one warp per vertex), below: 32-vertex tiles
+constexpr uint32_t kMidMinDeg = GVC_MID_MIN_DEG;      // >= : mid task (8 vertices per warp), below: 32-vertex tiles
 constexpr int kNumDegBins = 132;
 
 // Task layout of one shard, positions refer to `order` (vertices sorted by degree bin, descending).
 struct Schedule {
     uint32_t n_local;       // vertices of the shard
     uint32_t n_ring;        // order[0, n_ring)                ring tasks
-    uint32_t n_coop;        // order[n_ring, n_ring + n_coop)  mid-degree vertices, 8 per task
+    uint32_t n_mid;        // order[n_ring, n_ring + n_mid)  mid-degree vertices, 8 per task
     uint32_t n_ring_ctas;   // CTAs [0, n_ring_ctas) share the ring tasks before joining the task queue
-    uint32_t n_tiles;       // 32-vertex tiles over order[n_ring + n_coop, n_local)
-    uint32_t n_feat_tiles;  // 32-vertex feature tiles over order[0, n_ring + n_coop)
+    uint32_t n_tiles;       // 32-vertex tiles over order[n_ring + n_mid, n_local)
+    uint32_t n_feat_tiles;  // 32-vertex feature tiles over order[0, n_ring + n_mid)
 };
 
 // degree -> bin, monotone in the degree, 4 bins per octave
@@ -493,7 +494,7 @@ __device__ __noinline__ void gather1_tile(float *__restrict__ T, uint32_t *__res
     __syncwarp();
 }
 
-// ---- batches of the cooperative gathers (coop and ring tasks) --------------------------------
+// ---- 64-row batches of the ring tasks ----------------------------------------------------------
 struct BatchIds { uint32_t lo, hi; };   // lane l holds neighbour ids e0+l and e0+32+l
 
 __device__ __forceinline__ BatchIds coop_load_ids(const uint32_t *__restrict__ col, uint32_t e0, uint32_t end,
@@ -695,7 +696,7 @@ __device__ __noinline__ float coop_gather1_fast(const uint32_t *__restrict__ col
     return acc;
 }
 
-// ---- feature vectors of ring/coop vertices: feat[pos * 32 + k] ------------------------------------
+// ---- feature vectors of ring/mid vertices: feat[pos * 32 + k] -------------------------------------
 // width 16: lanes 0-15 hold agg[c], lanes 16-31 supply self[c] with the :38-40 quirk
 __device__ __forceinline__ void put_features16(float *__restrict__ feat, uint32_t pos, float acc,
                                                const float *__restrict__ in, uint32_t ul, uint32_t deg,
@@ -792,8 +793,8 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     // ---- dynamic tasks, one warp each ----------------------------------------------------------------
     // stage 0: front = the giants, one warp each; everything else is a 32-vertex tile.
     // stages 1/2: front = mid tasks (8 vertices each); tiles hold the vertices of degree < 64.
-    const uint32_t n_pre = STAGE == 0 ? sc.n_ring : sc.n_ring + sc.n_coop;   // positions that go through feature tiles
-    const uint32_t n_front = STAGE == 0 ? sc.n_ring : (sc.n_coop + 7) / 8;
+    const uint32_t n_pre = STAGE == 0 ? sc.n_ring : sc.n_ring + sc.n_mid;   // positions that go through feature tiles
+    const uint32_t n_front = STAGE == 0 ? sc.n_ring : (sc.n_mid + 7) / 8;
     const uint32_t n_tiles = (sc.n_local - n_pre + kTileVerts - 1) / kTileVerts;
     const uint32_t n_heavy = n_front + n_tiles;             // dealt alternately from both ends
     const uint32_t n_tasks = n_heavy + (n_pre + kTileVerts - 1) / kTileVerts;

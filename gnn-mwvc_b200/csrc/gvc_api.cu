@@ -260,7 +260,7 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     const uint32_t nl = c->n_local();
     if (nl == 0) return 0;
     const Schedule &sc = c->sched;
-    const uint32_t n_tasks = STAGE == 0 ? sc.n_ring + (nl - sc.n_ring + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
+    const uint32_t n_tasks = STAGE == 0 ? sc.n_giant1 + (nl - sc.n_giant1 + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
                                         : (sc.n_mid + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
     const unsigned want = std::max<unsigned>(STAGE == 0 ? 0u : sc.n_ring, (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
     const unsigned grid = std::max(1u, std::min<unsigned>(kCtasPerSm * c->num_sms, want));
@@ -311,9 +311,10 @@ int build_schedule(gvc_ctx *c) {
     uint32_t hist[kNumDegBins], start[kNumDegBins];
     GVC_CUDA(cudaMemcpyAsync(hist, c->d_bins.p, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));
-    uint32_t pos = 0, n_ring = 0, n_pre = 0;
+    uint32_t pos = 0, n_ring = 0, n_pre = 0, n_giant1 = 0;
     for (int b = kNumDegBins - 1; b >= 0; --b) {          // descending degree
         if (b == degree_bin(kRingMinDeg) - 1) n_ring = pos;
+        if (b == degree_bin(kGiant1MinDeg) - 1) n_giant1 = pos;
         if (b == degree_bin(kMidMinDeg) - 1) n_pre = pos;
         start[b] = pos;
         pos += hist[b];
@@ -321,6 +322,7 @@ int build_schedule(gvc_ctx *c) {
     Schedule &sc = c->sched;
     sc.n_local = nl;
     sc.n_ring = n_ring;
+    sc.n_giant1 = n_giant1;
     sc.n_mid = n_pre - n_ring;
     sc.n_tiles = (nl - n_pre + kTileVerts - 1) / kTileVerts;
     sc.n_feat_tiles = (n_pre + kTileVerts - 1) / kTileVerts;

@@ -78,7 +78,11 @@ constexpr int kWarpSmemFloats = kTileFloats + 32;   // tile + vid[32]
 #define GVC_MID_MIN_DEG 64
 #endif
 constexpr int kHeavyWarps = GVC_HEAVY_WARPS;    // warps per CTA that draw tasks from the heavy end of the list
-constexpr uint32_t kRingMinDeg = GVC_RING_MIN_DEG;    // >= : ring task (whole CTA)
+constexpr uint32_t kRingMinDeg = GVC_RING_MIN_DEG;
+#ifndef GVC_GIANT1_MIN_DEG
+#define GVC_GIANT1_MIN_DEG 2048
+#endif
+constexpr uint32_t kGiant1MinDeg = GVC_GIANT1_MIN_DEG;   // stage 0 (w = 1): >= one warp per vertex, below one lane    // >= : ring task (whole CTA)
 constexpr uint32_t kMidMinDeg = GVC_MID_MIN_DEG;      // >= : mid task (8 vertices per warp), below: 32-vertex tiles
 constexpr int kNumDegBins = 132;
 
@@ -88,6 +92,7 @@ struct Schedule {
     uint32_t n_ring;        // order[0, n_ring)                ring tasks
     uint32_t n_mid;        // order[n_ring, n_ring + n_mid)  mid-degree vertices, 8 per task
     uint32_t n_ring_ctas;   // CTAs [0, n_ring_ctas) share the ring tasks before joining the task queue
+    uint32_t n_giant1;      // order[0, n_giant1): deg >= kGiant1MinDeg, the single-warp tasks of stage 0 (w = 1)
     uint32_t n_tiles;       // 32-vertex tiles over order[n_ring + n_mid, n_local)
     uint32_t n_feat_tiles;  // 32-vertex feature tiles over order[0, n_ring + n_mid)
 };
@@ -793,8 +798,8 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     // ---- dynamic tasks, one warp each ----------------------------------------------------------------
     // stage 0: front = the giants, one warp each; everything else is a 32-vertex tile.
     // stages 1/2: front = mid tasks (8 vertices each); tiles hold the vertices of degree < 64.
-    const uint32_t n_pre = STAGE == 0 ? sc.n_ring : sc.n_ring + sc.n_mid;   // positions that go through feature tiles
-    const uint32_t n_front = STAGE == 0 ? sc.n_ring : (sc.n_mid + 7) / 8;
+    const uint32_t n_pre = STAGE == 0 ? sc.n_giant1 : sc.n_ring + sc.n_mid;   // positions that go through feature tiles
+    const uint32_t n_front = STAGE == 0 ? sc.n_giant1 : (sc.n_mid + 7) / 8;
     const uint32_t n_tiles = (sc.n_local - n_pre + kTileVerts - 1) / kTileVerts;
     const uint32_t n_heavy = n_front + n_tiles;             // dealt alternately from both ends
     const uint32_t n_tasks = n_heavy + (n_pre + kTileVerts - 1) / kTileVerts;

@@ -111,6 +111,7 @@ struct gvc_ctx {
     DevBuf<float> d_feat;
     gvc::Schedule sched{};
     int num_sms = 148;
+    int ctas_per_sm[3] = {1, 1, 1};      // resident CTAs per SM of each stage kernel (occupancy query)
 
     // activations
     DevBuf<float> d_x, d_h1, d_h2, d_scores, d_ping, d_pong;
@@ -263,7 +264,9 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     const uint32_t n_tasks = STAGE == 0 ? sc.n_giant1 + (nl - sc.n_giant1 + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
                                         : (sc.n_mid + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
     const unsigned want = std::max<unsigned>(STAGE == 0 ? 0u : sc.n_ring, (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
-    const unsigned grid = std::max(1u, std::min<unsigned>(kCtasPerSm * c->num_sms, want));
+    // persistent kernel: never more CTAs than can be resident at once (warps wait on each other's
+    // feature vectors; a CTA that is not running could never deliver its ring tasks)
+    const unsigned grid = std::max(1u, std::min<unsigned>(c->ctas_per_sm[STAGE] * c->num_sms, want));
     Schedule sc_launch = sc;
     sc_launch.n_ring_ctas = std::min<unsigned>(grid, (unsigned)c->num_sms);   // one ring CTA per SM at most
     const size_t smem = stage_smem_bytes<STAGE>();
@@ -337,10 +340,14 @@ int build_schedule(gvc_ctx *c) {
 }
 
 template <int STAGE>
-int set_stage_attrs() {
+int set_stage_attrs(gvc_ctx *c) {
     const int smem = (int)stage_smem_bytes<STAGE>();
     GVC_CUDA(cudaFuncSetAttribute(stage_kernel<STAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     GVC_CUDA(cudaFuncSetAttribute(stage_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int a = 0, b = 0;
+    GVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage_kernel<STAGE, true>, kCtaThreads, smem));
+    GVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage_kernel<STAGE, false>, kCtaThreads, smem));
+    c->ctas_per_sm[STAGE] = std::max(1, std::min(kCtasPerSm, std::min(a, b)));
     return 0;
 }
 
@@ -458,7 +465,7 @@ int gvc_ctx_create(gvc_ctx **out, int device) {
     if (e != cudaSuccess) { delete c; return fail(1000 + (int)e, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     c->stream = c->own_stream;
     int rc;
-    if ((rc = set_stage_attrs<0>()) || (rc = set_stage_attrs<1>()) || (rc = set_stage_attrs<2>())) {
+    if ((rc = set_stage_attrs<0>(c)) || (rc = set_stage_attrs<1>(c)) || (rc = set_stage_attrs<2>(c))) {
         cudaStreamDestroy(c->own_stream);
         delete c;
         return rc;

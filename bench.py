@@ -248,14 +248,14 @@ def run_ours(args):
     weight_scale = 200.0
     x_full = (g.weights.to(torch.float32) / weight_scale).contiguous()
     if world > 1:
-        # equal-sized shards of the cyclically relabelled graph: every world-th vertex per shard
-        g, _perm = graphs.cyclic_relabel(g, world)
+        # equal-sized, equal-work shards: vertices dealt to the shards in order of descending degree
+        g, _perm = graphs.balanced_relabel(g, world)
         x_full = (g.weights.to(torch.float32) / weight_scale).contiguous()
         per = g.n // world
         bounds = [r * per for r in range(world + 1)]
     else:
         bounds = [0, n]
-    shard = gdist.make_shard(g, bounds, rank)
+    shard = gdist.make_shard(g, bounds, rank, skip_isolated=world > 1)
     rp32 = shard.row_ptr.to(torch.int32).contiguous()
     g.eu = g.ev = None
     gen_s = time.perf_counter() - t0
@@ -313,9 +313,9 @@ def run_ours(args):
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
                 ev[0].record(stream)
                 ctx.stage_device(0, x_full, h1, weight_scale, mode); ev[1].record(stream)
-                gdist.exchange_rows(h1, bounds); ev[2].record(stream)
+                gdist.exchange_rows(h1, bounds, None, shard.live); ev[2].record(stream)
                 ctx.stage_device(1, h1, h2, weight_scale, mode); ev[3].record(stream)
-                gdist.exchange_rows(h2, bounds); ev[4].record(stream)
+                gdist.exchange_rows(h2, bounds, None, shard.live); ev[4].record(stream)
                 ctx.stage_device(2, h2, scores, weight_scale, mode); ev[5].record(stream)
                 ev[5].synchronize()
                 for i, k in enumerate(names):
@@ -363,16 +363,47 @@ def run_ours(args):
     e2e = None
     x_host = x_full.cpu().numpy()
     if world == 1:
+        k = max(3, min(args.steps, 50))
+        # (i) CSR resident: per step only x goes up and the scores come back
         for _ in range(3):
             ctx.forward(x_host, weight_scale, mode)
-        k = max(3, min(args.steps, 50))
         t1 = time.perf_counter()
         for _ in range(k):
             out_host = ctx.forward(x_host, weight_scale, mode)
+        res_s = (time.perf_counter() - t1) / k
+        # (ii) the whole predict() input per step, as the drop-in calls the ABI: the CSR sits in
+        # the context's pinned host buffers (where the drop-in's extraction writes it) and is
+        # uploaded -- copies, checks, degree schedule -- inside the timed region, then forward
+        srp, scol, sW, sNW = ctx.graph_staging(n, m)
+        srp[:] = shard.row_ptr.cpu().numpy()
+        scol[:] = shard.col.cpu().numpy().view(np.uint32)
+        sW[:] = shard.weights.cpu().numpy().view(np.uint32)
+        sNW[:] = shard.nw.cpu().numpy().view(np.uint32)
+
+        def cold_step():
+            ctx.graph_upload(srp, scol, sW, sNW)
+            return ctx.forward(x_host, weight_scale, mode)
+        for _ in range(3):
+            cold_step()
+        t1 = time.perf_counter()
+        for _ in range(k):
+            out_cold = cold_step()
         e2e_s = (time.perf_counter() - t1) / k
-        e2e = {"value": max(e_total, 1) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * n),
-               "d2h_bytes_per_step": int(4 * n), "ms_per_step": e2e_s * 1e3,
-               "what": "gvc_forward(): pinned H2D of x, 3 fused kernels, D2H of the scores; CSR resident (uploaded once)"}
+        assert np.array_equal(out_cold.view(np.uint32), out_host.view(np.uint32))
+        t1 = time.perf_counter()
+        for _ in range(k):
+            ctx.graph_upload(srp, scol, sW, sNW)
+        up_s = (time.perf_counter() - t1) / k
+        h2d = int(srp.nbytes + scol.nbytes + sW.nbytes + sNW.nbytes + 4 * n)
+        e2e = {"value": max(e_total, 1) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(4 * n), "ms_per_step": e2e_s * 1e3, "graph_upload_ms": up_s * 1e3,
+               "graph_upload_GBps": (h2d - 4 * n) / up_s / 1e9,
+               "what": "gvc_graph_upload() + gvc_forward() per step, host buffers in, host scores out: H2D of the "
+                       "whole CSR from pinned host memory + x, id/offset checks, degree schedule, 3 fused kernels, "
+                       "D2H of the scores",
+               "csr_resident": {"value": max(e_total, 1) / res_s, "unit": UNIT, "ms_per_step": res_s * 1e3,
+                                "h2d_bytes_per_step": int(4 * n), "d2h_bytes_per_step": int(4 * n),
+                                "what": "gvc_forward() only: H2D of x, 3 fused kernels, D2H of the scores; CSR uploaded once"}}
         assert np.isfinite(out_host).all()
     else:
         xp = torch.from_numpy(x_host).pin_memory()
@@ -427,7 +458,7 @@ def run_ours(args):
             "config": {"workload": wl_name, "vertices": n, "edges": e_total, "nnz": m, "mode": args.mode,
                        "weights": "trained GNN_VC model (tests/golden/mwvc_model.npz)",
                        "l2": "256 MiB flush write between timed steps; working set (CSR + rows) also exceeds the 126 MB L2",
-                       "sharding": "single GPU" if world == 1 else f"{world} equal vertex ranges of the cyclically relabelled graph (v -> shard v % {world}), NCCL all-gather of 16-float rows after stages 0 and 1",
+                       "sharding": "single GPU" if world == 1 else f"{world} equal vertex ranges of the relabelled graph (vertices dealt to the shards by descending degree: equal counts, equal nnz), NCCL all-gather of the 16-float rows of the non-isolated vertices after stages 0 and 1",
                        "graph_generation_s": round(gen_s, 2)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "phase_ms": phase_ms, "other_mode": other,

@@ -32,6 +32,8 @@ SIGNATURES = {
     "gvc_model_is_fused": (C.c_int, [C.c_void_p]),
     "gvc_graph_upload": (C.c_int, [C.c_void_p, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
     "gvc_graph_upload_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
+    "gvc_graph_staging": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(_u64p), C.POINTER(_u32p),
+                                    C.POINTER(_u32p), C.POINTER(_u32p)]),
     "gvc_graph_adopt_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gvc_graph_set_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "gvc_forward": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, C.c_int]),
@@ -166,6 +168,14 @@ class Context:
         self._check(self.lib.gvc_graph_upload_shard(self.h, n_global, v_begin, v_end, _ptr(row_ptr, _u64p),
                                                     _ptr(col, _u32p), _ptr(W, _u32p), _ptr(NW, _u32p)))
         self.n_global, self.v_begin, self.v_end = n_global, v_begin, v_end
+
+    def graph_staging(self, n_local: int, nnz: int):
+        """Pinned host buffers of the context as numpy views (row_ptr u64, col, W, NW u32): fill
+        them and hand them to graph_upload for DMA-speed uploads."""
+        rp, col, W, NW = _u64p(), _u32p(), _u32p(), _u32p()
+        self._check(self.lib.gvc_graph_staging(self.h, n_local, nnz, C.byref(rp), C.byref(col), C.byref(W), C.byref(NW)))
+        view = lambda p, k: np.ctypeslib.as_array(p, shape=(max(k, 1),))[:k]
+        return view(rp, n_local + 1), view(col, nnz), view(W, n_local), view(NW, n_local)
 
     def graph_adopt(self, row_ptr_i32, col_i32, W_i32, NW_i32, n_global=None, v_begin=0, v_end=None):
         """Device-resident shard: torch int32 CUDA tensors (bit patterns of uint32)."""

@@ -13,6 +13,8 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -83,6 +85,20 @@ struct PinBuf {   // grow-only pinned host buffer
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// GVC_TRACE=1: wall time of the steps of an upload on stderr (synchronises at every step)
+struct Tracer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    Tracer() : on(std::getenv("GVC_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void tick(const char *what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        auto n = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "gvc trace: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 }  // namespace
 
 struct gvc_ctx {
@@ -104,7 +120,12 @@ struct gvc_ctx {
     uint64_t nnz = 0;
     const uint32_t *row_ptr = nullptr, *col = nullptr, *Wv = nullptr, *NWv = nullptr;   // device views
     DevBuf<uint32_t> own_row_ptr, own_col, own_W, own_NW;
-    PinBuf<uint32_t> stage_u32;
+    DevBuf<uint64_t> d_row_ptr64;        // the ABI's 64-bit offsets, narrowed and checked on the device
+    DevBuf<uint32_t> d_flag;             // upload validation result (kBadRowPtr | kBadCol)
+    PinBuf<uint64_t> stg_row_ptr;        // gvc_graph_staging: pinned host buffers the caller fills
+    PinBuf<uint32_t> stg_col, stg_W, stg_NW;
+    cudaStream_t copy_stream = nullptr;  // the adjacency travels here while the schedule is built on `stream`
+    cudaEvent_t ev_begin = nullptr, ev_copy = nullptr;
     // schedule (gvc_kernels.cuh): vertices counting-sorted by degree bin + tile classes
     DevBuf<uint32_t> d_order, d_bins, d_sync;
     DevBuf<uint4> d_vrec;
@@ -271,7 +292,7 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     sc_launch.n_ring_ctas = std::min<unsigned>(grid, (unsigned)c->num_sms);   // one ring CTA per SM at most
     const size_t smem = stage_smem_bytes<STAGE>();
     // task counter + per-feature-tile completion counters start at zero
-    GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (3 + (size_t)sc.n_feat_tiles) * sizeof(uint32_t), c->stream));
+    GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (kSyncCounters + (size_t)sc.n_feat_tiles) * sizeof(uint32_t), c->stream));
     if (mode == GVC_MODE_EXACT) {
         stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
             c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
@@ -294,6 +315,35 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
         c->launches++;
     }
     return 0;
+}
+
+// ---- upload-time checks, on the device (the arrays are there anyway) -----------------------
+constexpr uint32_t kBadRowPtr = 1u, kBadCol = 2u;
+
+// 64-bit ABI offsets -> the 32-bit layout the kernels read; flags a non-monotone array
+__global__ void narrow_row_ptr_kernel(const uint64_t *__restrict__ rp64, uint32_t n_local, uint64_t nnz,
+                                      uint32_t *__restrict__ rp32, uint32_t *__restrict__ flag) {
+    bool bad = false;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u <= n_local; u += gridDim.x * blockDim.x) {
+        const uint64_t v = rp64[u];
+        rp32[u] = (uint32_t)v;
+        if (v > nnz || (u < n_local && rp64[u + 1] < v)) bad = true;
+    }
+    if (bad) atomicOr(flag, kBadRowPtr);
+}
+
+// every neighbour id must name a vertex of the global graph (the gather would read outside h)
+__global__ void check_col_kernel(const uint32_t *__restrict__ col, uint64_t nnz, uint32_t n_global,
+                                 uint32_t *__restrict__ flag) {
+    bool bad = false;
+    const uint64_t n4 = nnz / 4;
+    const uint4 *c4 = reinterpret_cast<const uint4 *>(col);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = c4[i];
+        bad |= (v.x >= n_global) | (v.y >= n_global) | (v.z >= n_global) | (v.w >= n_global);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (nnz & 3)) bad |= col[n4 * 4 + threadIdx.x] >= n_global;
+    if (bad) atomicOr(flag, kBadCol);
 }
 
 // Degree schedule of the shard's vertices (see gvc_kernels.cuh).  Part of the graph upload:
@@ -330,7 +380,7 @@ int build_schedule(gvc_ctx *c) {
     sc.n_tiles = (nl - n_pre + kTileVerts - 1) / kTileVerts;
     sc.n_feat_tiles = (n_pre + kTileVerts - 1) / kTileVerts;
     if ((rc = c->d_feat.reserve((size_t)n_pre * 32))) return rc;
-    if ((rc = c->d_sync.reserve(3 + (size_t)sc.n_feat_tiles))) return rc;
+    if ((rc = c->d_sync.reserve(kSyncCounters + (size_t)sc.n_feat_tiles))) return rc;
     GVC_CUDA(cudaMemcpyAsync(c->d_bins.p, start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
     degree_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, c->Wv, nl, c->d_bins.p, c->d_order.p, c->d_vrec.p);
     GVC_CUDA(cudaGetLastError());
@@ -442,7 +492,7 @@ int set_graph_views(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_
 extern "C" {
 
 const char *gvc_last_error(void) { return g_err.c_str(); }
-int gvc_abi_version(void) { return 1; }
+int gvc_abi_version(void) { return 2; }
 
 int gvc_ctx_create(gvc_ctx **out, int device) {
     if (!out) return fail(GVC_ERR_ARG, "out is null");
@@ -464,8 +514,15 @@ int gvc_ctx_create(gvc_ctx **out, int device) {
     e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(1000 + (int)e, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     c->stream = c->own_stream;
-    int rc;
-    if ((rc = set_stage_attrs<0>(c)) || (rc = set_stage_attrs<1>(c)) || (rc = set_stage_attrs<2>(c))) {
+    int rc = 0;
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->ev_begin, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming)) != cudaSuccess)
+        rc = fail(1000 + (int)e, "copy stream/events: %s", cudaGetErrorString(e));
+    if (rc || (rc = set_stage_attrs<0>(c)) || (rc = set_stage_attrs<1>(c)) || (rc = set_stage_attrs<2>(c))) {
+        if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+        if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         cudaStreamDestroy(c->own_stream);
         delete c;
         return rc;
@@ -478,14 +535,19 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
     for (auto &l : c->layers) { if (l.dW) cudaFree(l.dW); if (l.db) cudaFree(l.db); }
     for (auto &p : c->d_stage_params) if (p) cudaFree(p);
     c->own_row_ptr.release(); c->own_col.release(); c->own_W.release(); c->own_NW.release();
-    c->stage_u32.release();
+    c->d_row_ptr64.release(); c->d_flag.release();
+    c->stg_row_ptr.release(); c->stg_col.release(); c->stg_W.release(); c->stg_NW.release();
     c->d_order.release(); c->d_vrec.release(); c->d_bins.release(); c->d_sync.release(); c->d_feat.release();
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
     c->d_ping.release(); c->d_pong.release();
     c->pin_x.release(); c->pin_scores.release();
+    cudaEventDestroy(c->ev_begin);
+    cudaEventDestroy(c->ev_copy);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -542,25 +604,73 @@ int gvc_graph_upload_shard(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
     if (nl && row_ptr[0] != 0) return fail(GVC_ERR_ARG, "row_ptr[0] must be 0");
     if (nnz >= (1ull << 32)) return fail(GVC_ERR_UNSUPPORTED, "shard has %llu adjacency entries; 2^32 is the limit", (unsigned long long)nnz);
     if (nnz && !col) return fail(GVC_ERR_ARG, "null col");
+    Tracer tr;
     if ((rc = c->own_row_ptr.reserve((size_t)nl + 1))) return rc;
     if ((rc = c->own_col.reserve(nnz + 4))) return rc;      // readable up to the next multiple of four ids
     if ((rc = c->own_W.reserve(nl))) return rc;
     if ((rc = c->own_NW.reserve(nl))) return rc;
-    // narrow the 64-bit offsets to the 32-bit layout the kernels read (pinned staging)
-    if ((rc = c->stage_u32.reserve((size_t)nl + 1))) return rc;
-    c->stage_u32.p[0] = 0;
-    for (uint32_t u = 0; u < nl; ++u) {
-        if (row_ptr[u + 1] < row_ptr[u]) return fail(GVC_ERR_ARG, "row_ptr not monotone at %u", u);
-        c->stage_u32.p[u + 1] = (uint32_t)row_ptr[u + 1];
-    }
-    GVC_CUDA(cudaMemcpyAsync(c->own_row_ptr.p, c->stage_u32.p, ((size_t)nl + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-    if (nnz) GVC_CUDA(cudaMemcpyAsync(c->own_col.p, col, nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = c->d_row_ptr64.reserve((size_t)nl + 1))) return rc;
+    if ((rc = c->d_flag.reserve(1))) return rc;
+    c->have_graph = false;
+    tr.tick("upload: device buffers");
+    // The adjacency (nearly all of the bytes) travels on the copy stream while the offsets are
+    // narrowed and the degree schedule is built on the compute stream.  From the pinned buffers
+    // of gvc_graph_staging both run as DMA; from pageable memory the copies stage through the
+    // driver and the calls serialise, with the same result.
+    GVC_CUDA(cudaMemsetAsync(c->d_flag.p, 0, sizeof(uint32_t), c->stream));
+    GVC_CUDA(cudaEventRecord(c->ev_begin, c->stream));                 // earlier forwards are done with own_col
+    GVC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_begin, 0));
     if (nl) {
+        GVC_CUDA(cudaMemcpyAsync(c->d_row_ptr64.p, row_ptr, ((size_t)nl + 1) * 8, cudaMemcpyHostToDevice, c->stream));
         GVC_CUDA(cudaMemcpyAsync(c->own_W.p, W, (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
         GVC_CUDA(cudaMemcpyAsync(c->own_NW.p, NW, (size_t)nl * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    GVC_CUDA(cudaStreamSynchronize(c->stream));
-    return set_graph_views(c, n_global, v_begin, v_end, c->own_row_ptr.p, c->own_col.p, c->own_W.p, c->own_NW.p, nnz);
+    if (nnz) {
+        GVC_CUDA(cudaMemcpyAsync(c->own_col.p, col, nnz * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        check_col_kernel<<<(unsigned)std::min<uint64_t>(1184, (nnz / 4 + 255) / 256 + 1), 256, 0, c->copy_stream>>>(c->own_col.p, nnz, n_global, c->d_flag.p);
+        GVC_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    GVC_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
+    tr.tick("upload: copies + id check");
+    if (nl) {
+        narrow_row_ptr_kernel<<<std::min<unsigned>(1184, nl / 256 + 1), 256, 0, c->stream>>>(c->d_row_ptr64.p, nl, nnz, c->own_row_ptr.p, c->d_flag.p);
+        GVC_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    tr.tick("upload: narrow offsets");
+    if ((rc = set_graph_views(c, n_global, v_begin, v_end, c->own_row_ptr.p, c->own_col.p, c->own_W.p, c->own_NW.p, nnz))) {
+        cudaStreamSynchronize(c->copy_stream);
+        c->have_graph = false;
+        return rc;
+    }
+    tr.tick("upload: schedule");
+    GVC_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));           // forwards start after the adjacency landed
+    uint32_t flag = 0;
+    GVC_CUDA(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));                        // also: the caller's buffers are free again
+    if (flag) {
+        c->have_graph = false;
+        if (flag & kBadRowPtr) return fail(GVC_ERR_ARG, "row_ptr is not monotone or exceeds row_ptr[n]");
+        return fail(GVC_ERR_ARG, "a neighbour id is >= %u vertices", n_global);
+    }
+    return 0;
+}
+
+int gvc_graph_staging(gvc_ctx *c, uint32_t n_local, uint64_t nnz, uint64_t **row_ptr, uint32_t **col,
+                      uint32_t **W, uint32_t **NW) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!row_ptr || !col || !W || !NW) return fail(GVC_ERR_ARG, "null out pointer");
+    if ((rc = use_device(c))) return rc;
+    Tracer tr;
+    if ((rc = c->stg_row_ptr.reserve((size_t)n_local + 1))) return rc;
+    if ((rc = c->stg_col.reserve(nnz + 4))) return rc;
+    if ((rc = c->stg_W.reserve((size_t)n_local + 1))) return rc;
+    if ((rc = c->stg_NW.reserve((size_t)n_local + 1))) return rc;
+    tr.tick("staging: pinned buffers");
+    *row_ptr = c->stg_row_ptr.p; *col = c->stg_col.p; *W = c->stg_W.p; *NW = c->stg_NW.p;
+    return 0;
 }
 
 int gvc_graph_upload(gvc_ctx *c, uint32_t n, const uint64_t *row_ptr, const uint32_t *col,
@@ -647,13 +757,16 @@ int gvc_forward(gvc_ctx *c, const float *x, float scale, float *scores, int mode
     if (n == 0) return 0;
     if (!x || !scores) return fail(GVC_ERR_ARG, "null buffer");
     if ((rc = use_device(c))) return rc;
+    Tracer tr;
     if ((rc = c->pin_x.reserve(n))) return rc;
     if ((rc = c->pin_scores.reserve(n))) return rc;
+    tr.tick("forward: pinned x/scores");
     std::memcpy(c->pin_x.p, x, (size_t)n * sizeof(float));
     GVC_CUDA(cudaMemcpyAsync(c->d_x.p, c->pin_x.p, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     if ((rc = gvc_forward_device(c, c->d_x.p, scale, c->d_scores.p, mode))) return rc;
     GVC_CUDA(cudaMemcpyAsync(c->pin_scores.p, c->d_scores.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));
+    tr.tick("forward: copies + kernels");
     std::memcpy(scores, c->pin_scores.p, (size_t)n * sizeof(float));
     return 0;
 }

@@ -64,6 +64,7 @@ constexpr int kTileStride = 36;           // floats per k-row of a tile (32 + 4 
 constexpr int kTileRows = 32;             // widest activation
 constexpr int kTileFloats = kTileRows * kTileStride;
 constexpr int kWarpSmemFloats = kTileFloats + 32;   // tile + vid[32]
+constexpr int kSyncCounters = 4;          // sync[0..2] task claims, sync[3] ring claims; then the feature-tile counters
 
 #ifndef GVC_MID_SETS
 #define GVC_MID_SETS 2            // row sets of 4 in flight per vertex in the mid tasks (3 and 4 measured slower)
@@ -566,15 +567,24 @@ __device__ __noinline__ void ring_gather16_exact(float *__restrict__ S, float *_
                                               const uint32_t *__restrict__ col,
                                               const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
                                               int warp, int lane) {
+    constexpr uint32_t kStep = 64 * kWarpsPerCta;
     const uint32_t nb = (end - beg + 63) / 64;
-    float4 r[8];
-    uint32_t b = warp;
-    BatchIds ids = coop_load_ids(col, beg + 64 * b, end, lane);
+    // Two batches of rows per warp are in flight: the rows of this warp's NEXT batch are requested
+    // before it waits for the running sum of the current one, so the memory latency of a batch is
+    // spread over two trips of the token around the ring (ids run two batches ahead of the rows).
+    // `endk` = end while batch b + 8k exists, else 0: loads past the list are predicated off.
+    auto end_of = [&](uint32_t bb) { return bb < nb ? end : 0u; };
+    float4 r[8], rn[8];
+    uint32_t b = warp, e0 = beg + 64 * b;
+    BatchIds ids = coop_load_ids(col, e0, end_of(b), lane);
+    BatchIds idn = coop_load_ids(col, e0 + kStep, end_of(b + kWarpsPerCta), lane);
+    coop_load_rows16(r, ids, in4, e0, end_of(b), lane);
+    ids = coop_load_ids(col, e0 + 2 * kStep, end_of(b + 2 * kWarpsPerCta), lane);
 #pragma unroll 1
-    for (; b < nb; b += kWarpsPerCta) {
-        const uint32_t e0 = beg + 64 * b;
-        coop_load_rows16(r, ids, in4, e0, end, lane);
-        ids = coop_load_ids(col, e0 + 64 * kWarpsPerCta, end, lane);   // this warp's next batch
+    for (; b < nb; b += kWarpsPerCta, e0 += kStep) {
+        coop_load_rows16(rn, idn, in4, e0 + kStep, end_of(b + kWarpsPerCta), lane);
+        idn = ids;
+        ids = coop_load_ids(col, e0 + 3 * kStep, end_of(b + 3 * kWarpsPerCta), lane);
         coop_stage_rows16(S, r, lane);
         __syncwarp();
         float acc = 0.0f;
@@ -586,6 +596,8 @@ __device__ __noinline__ void ring_gather16_exact(float *__restrict__ S, float *_
         __syncwarp();
         if (lane < 16) ring_acc[lane] = acc;
         if (b + 1 < nb) named_bar_arrive(1 + (int)((b + 1) % kWarpsPerCta), 64);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r[w] = rn[w];
     }
 }
 
@@ -596,18 +608,25 @@ __device__ __noinline__ void ring_gather16_exact(float *__restrict__ S, float *_
 __device__ __noinline__ void ring_gather16_fast(float *__restrict__ part, const uint32_t *__restrict__ col,
                                                 const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
                                                 int warp, int lane) {
+    constexpr uint32_t kStep = 64 * kWarpsPerCta;
     const uint32_t nb = (end - beg + 63) / 64;
+    auto end_of = [&](uint32_t bb) { return bb < nb ? end : 0u; };
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 r[8];
-    uint32_t b = warp;
-    BatchIds ids = coop_load_ids(col, beg + 64 * b, end, lane);
+    float4 r[8], rn[8];
+    uint32_t b = warp, e0 = beg + 64 * b;
+    BatchIds ids = coop_load_ids(col, e0, end_of(b), lane);
+    BatchIds idn = coop_load_ids(col, e0 + kStep, end_of(b + kWarpsPerCta), lane);
+    coop_load_rows16(r, ids, in4, e0, end_of(b), lane);          // rows past `end` come back as zeros
+    ids = coop_load_ids(col, e0 + 2 * kStep, end_of(b + 2 * kWarpsPerCta), lane);
 #pragma unroll 1
-    for (; b < nb; b += kWarpsPerCta) {
-        const uint32_t e0 = beg + 64 * b;
-        coop_load_rows16(r, ids, in4, e0, end, lane);          // rows past `end` come back as zeros
-        ids = coop_load_ids(col, e0 + 64 * kWarpsPerCta, end, lane);
+    for (; b < nb; b += kWarpsPerCta, e0 += kStep) {
+        coop_load_rows16(rn, idn, in4, e0 + kStep, end_of(b + kWarpsPerCta), lane);   // next batch in flight
+        idn = ids;
+        ids = coop_load_ids(col, e0 + 3 * kStep, end_of(b + 3 * kWarpsPerCta), lane);
 #pragma unroll
         for (int w = 0; w < 8; ++w) { acc.x += r[w].x; acc.y += r[w].y; acc.z += r[w].z; acc.w += r[w].w; }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r[w] = rn[w];
     }
 #pragma unroll
     for (int m = 4; m < 32; m <<= 1) {                         // the 8 sub-warps hold the same 4 columns
@@ -619,37 +638,53 @@ __device__ __noinline__ void ring_gather16_fast(float *__restrict__ part, const 
 
 // ---- width 1 ---------------------------------------------------------------------------------------
 // single-warp task, width 1 (stage 0 giants): blocks of 256 neighbours, lane l holds elements
-// 32 t + l (coalesced ids, gathered x).  The ids of block b+2 and the values of block b+1 are
-// in flight while block b is summed.  The block is parked in shared memory and every lane
-// walks it with broadcast 128-bit loads (one dependent FADD per neighbour, ~4 cycles), which
-// covers the memory latency of the next block.
+// 32 t + l (coalesced ids, gathered x).  The chain needs ~4 cycles per neighbour (one dependent
+// FADD), about 0.5 us per block, a gather under load takes several times that: the values of the
+// next kGiant1Depth blocks and the ids of two blocks beyond those are in flight while a block is
+// summed.  The block is parked in shared memory and every lane walks it with broadcast 128-bit
+// loads.
+constexpr int kGiant1Depth = 4;
+
 __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 floats */,
                                               const uint32_t *__restrict__ col, const float *__restrict__ x,
                                               uint32_t beg, uint32_t end, int lane) {
     float acc = 0.0f;
     if (beg >= end) return acc;
-    uint32_t idn[8], idnn[8];
-    float v[8], vn[8];
-    auto ld_ids = [&](uint32_t (&id)[8], uint32_t e0) {
+    constexpr int K = kGiant1Depth;
+    const uint32_t nb = (end - beg + 255) / 256;
+    uint32_t ida[8], idb[8];           // ids of blocks b + K and b + K + 1
+    float v[K][8];                     // values of blocks b .. b + K - 1
+    auto ld_ids = [&](uint32_t (&id)[8], uint32_t blk) {
+        const uint32_t e0 = beg + 256 * blk, lim = blk < nb ? end : 0u;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < end) ? ld_id(col + e) : 0u; }
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < lim) ? ld_id(col + e) : 0u; }
     };
-    auto ld_x = [&](float (&val)[8], const uint32_t (&id)[8], uint32_t e0) {
+    auto ld_x = [&](float (&val)[8], const uint32_t (&id)[8], uint32_t blk) {
+        const uint32_t e0 = beg + 256 * blk, lim = blk < nb ? end : 0u;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; val[t] = (e < end) ? __ldg(x + id[t]) : 0.0f; }
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; val[t] = (e < lim) ? __ldg(x + id[t]) : 0.0f; }
     };
-    ld_ids(idn, beg);
-    ld_ids(idnn, beg + 256);
-    ld_x(v, idn, beg);
-    ld_ids(idn, beg + 512);                       // idn: block 2, idnn: block 1
+#pragma unroll
+    for (int k = 0; k < K; ++k) {      // prologue: ids then values of the first K blocks
+        ld_ids(ida, k);
+        ld_x(v[k], ida, k);
+    }
+    ld_ids(ida, K);
+    ld_ids(idb, K + 1);
 #pragma unroll 1
-    for (uint32_t e0 = beg; e0 < end; e0 += 256) {
+    for (uint32_t blk = 0; blk < nb; ++blk) {
+        const uint32_t e0 = beg + 256 * blk;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) S[32 * t + lane] = v[t];
-        ld_x(vn, idnn, e0 + 256);                 // values of the next block
+        for (int t = 0; t < 8; ++t) S[32 * t + lane] = v[0][t];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) idnn[t] = idn[t];
-        ld_ids(idn, e0 + 768);                    // ids two blocks further
+        for (int k = 0; k + 1 < K; ++k) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[k][t] = v[k + 1][t];
+        }
+        ld_x(v[K - 1], ida, blk + K);             // values K blocks ahead
+#pragma unroll
+        for (int t = 0; t < 8; ++t) ida[t] = idb[t];
+        ld_ids(idb, blk + K + 2);
         __syncwarp();
         const int cnt = (int)min(256u, end - e0);
         const float4 *s4 = reinterpret_cast<const float4 *>(S);
@@ -661,12 +696,12 @@ __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 float
 #pragma unroll 4
             for (; j < 256; j += 16) {
                 const int n4 = (j + 16 < 256) ? (j + 16) / 4 : 0;
-                const float4 na = s4[n4], nb = s4[n4 + 1], nc = s4[n4 + 2], nd = s4[n4 + 3];
+                const float4 na = s4[n4], nb4 = s4[n4 + 1], nc = s4[n4 + 2], nd = s4[n4 + 3];
                 acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
                 acc = __fadd_rn(acc, b.x); acc = __fadd_rn(acc, b.y); acc = __fadd_rn(acc, b.z); acc = __fadd_rn(acc, b.w);
                 acc = __fadd_rn(acc, c.x); acc = __fadd_rn(acc, c.y); acc = __fadd_rn(acc, c.z); acc = __fadd_rn(acc, c.w);
                 acc = __fadd_rn(acc, d.x); acc = __fadd_rn(acc, d.y); acc = __fadd_rn(acc, d.z); acc = __fadd_rn(acc, d.w);
-                a = na; b = nb; c = nc; d = nd;
+                a = na; b = nb4; c = nc; d = nd;
             }
         }
         for (; j + 16 <= cnt; j += 16) {
@@ -678,8 +713,6 @@ __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 float
         }
         for (; j < cnt; ++j) acc = __fadd_rn(acc, S[j]);
         __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = vn[t];
     }
     return acc;
 }
@@ -741,7 +774,8 @@ __device__ __forceinline__ void publish_feature(uint32_t *__restrict__ ready, ui
 // STAGE 0: in = x [n_global],      out = h rows [n_global x 16]
 // STAGE 1: in = h [n_global x 16], out = h rows [n_global x 16]
 // STAGE 2: in = h [n_global x 16], out = scores [n_local]
-// sync[0..2] = task counters, sync[3 + t] = finished feature vectors of feature tile t; zeroed before launch.
+// sync[0..2] = task counters, sync[3] = ring claims, sync[4 + t] = finished feature vectors of feature
+// tile t; zeroed before launch.
 template <int STAGE, bool EXACT>
 __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
@@ -754,8 +788,8 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     extern __shared__ __align__(16) float smem[];
     float *P = smem;                                             // packed parameters
     constexpr int kParamFloats = (D.floats() + 3) / 4 * 4;
-    float *ring_acc = smem + kParamFloats;                       // 16 floats
-    float *warp_mem = ring_acc + 16;
+    float *ring_acc = smem + kParamFloats;                       // 16 floats + the CTA's ring claim
+    float *warp_mem = ring_acc + 20;
 
     for (int i = threadIdx.x; i < D.floats(); i += kCtaThreads) P[i] = __ldg(params + i);
     __syncthreads();
@@ -763,14 +797,20 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *T = warp_mem + warp * kWarpSmemFloats;
     uint32_t *vid = reinterpret_cast<uint32_t *>(T + kTileFloats);
-    uint32_t *ready = sync + 3;
+    uint32_t *ready = sync + kSyncCounters;
 
     // ---- ring tasks (width 16 only): the whole CTA, largest vertices first --------------------
     // With w = 1 the chain costs the same 4 cycles per neighbour whoever feeds it and one warp
     // can keep its own loads ahead, so stage 0 runs the giants as single-warp tasks instead.
     if constexpr (STAGE != 0) {
+        // claimed one at a time, largest first: a CTA that drew a huge vertex takes fewer of them
+        uint32_t *claim = reinterpret_cast<uint32_t *>(ring_acc) + 16;
 #pragma unroll 1
-        for (uint32_t g = blockIdx.x; blockIdx.x < sc.n_ring_ctas && g < sc.n_ring; g += sc.n_ring_ctas) {
+        while (blockIdx.x < sc.n_ring_ctas && sc.n_ring) {
+            if (threadIdx.x == 0) *claim = atomicAdd(sync + 3, 1u);
+            __syncthreads();
+            const uint32_t g = *claim;
+            if (g >= sc.n_ring) break;
             const uint32_t ul = __ldg(order + g);
             const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
             if constexpr (EXACT) {
@@ -871,7 +911,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
 template <int STAGE>
 constexpr size_t stage_smem_bytes() {
     constexpr StageDims D = stage_dims(STAGE);
-    return ((D.floats() + 3) / 4 * 4 + 16 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
+    return ((D.floats() + 3) / 4 * 4 + 20 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
 }
 
 // ---- schedule construction (graph upload time) -------------------------------------------

@@ -31,6 +31,7 @@ class Shard:
     col: torch.Tensor       # int32 [nnz_local], global ids
     weights: torch.Tensor   # int32 [n_local]
     nw: torch.Tensor        # int32 [n_local]
+    live: list = None       # per rank: leading rows that other ranks may read (None: all of them)
 
     @property
     def n_local(self) -> int:
@@ -41,24 +42,34 @@ class Shard:
         return int(self.col.numel())
 
 
-def make_shard(g, bounds, rank: int) -> Shard:
-    """Cut rank's vertex range out of a whole graph (graphs.Graph) that lives on any device."""
+def make_shard(g, bounds, rank: int, skip_isolated: bool = False) -> Shard:
+    """Cut rank's vertex range out of a whole graph (graphs.Graph) that lives on any device.
+    skip_isolated (symmetric graphs only): exchange just the leading rows of every shard that
+    hold non-isolated vertices (graphs.live_rows)."""
+    from . import graphs
     a, b = bounds[rank], bounds[rank + 1]
     lo, hi = int(g.row_ptr[a].item()), int(g.row_ptr[b].item())
     return Shard(n_global=g.n, v_begin=a, v_end=b, bounds=list(bounds),
                  row_ptr=(g.row_ptr[a:b + 1] - lo).contiguous(),
                  col=g.col[lo:hi].contiguous(), weights=g.weights[a:b].contiguous(),
-                 nw=g.nw[a:b].contiguous())
+                 nw=g.nw[a:b].contiguous(),
+                 live=graphs.live_rows(g.row_ptr, bounds) if skip_isolated else None)
 
 
-def exchange_rows(full: torch.Tensor, bounds, group=None) -> None:
+def exchange_rows(full: torch.Tensor, bounds, group=None, live=None) -> None:
     """All-gather of row slices, in place: on entry ``full[bounds[r]:bounds[r+1]]`` is valid on
-    rank r; on return every rank holds all rows.  Slices may differ in length."""
+    rank r; on return every rank holds all rows.  Slices may differ in length.  With ``live``
+    only the first live[r] rows of every slice travel (the rest is never read remotely)."""
     world = dist.get_world_size(group)
     if world == 1:
         return
     rank = dist.get_rank(group)
-    views = [full[bounds[r]:bounds[r + 1]] for r in range(world)]
+    if live is None:
+        views = [full[bounds[r]:bounds[r + 1]] for r in range(world)]
+    else:
+        # equal prefixes keep the single collective; a row more than needed does no harm
+        same = max(live) if max(live) <= min(bounds[r + 1] - bounds[r] for r in range(world)) else None
+        views = [full[bounds[r]:bounds[r] + (same if same is not None else live[r])] for r in range(world)]
     sizes = {v.shape[0] for v in views}
     if len(sizes) == 1:
         dist.all_gather(views, views[rank], group=group)          # equal slices: one collective
@@ -80,11 +91,11 @@ def sharded_forward(stage_fn, shard: Shard, x_full: torch.Tensor, h1: torch.Tens
     stage_fn(0, x_full, h1, weight_scale, mode)
     if before_exchange:
         before_exchange()
-    exchange_rows(h1, shard.bounds, group)
+    exchange_rows(h1, shard.bounds, group, shard.live)
     stage_fn(1, h1, h2, weight_scale, mode)
     if before_exchange:
         before_exchange()
-    exchange_rows(h2, shard.bounds, group)
+    exchange_rows(h2, shard.bounds, group, shard.live)
     stage_fn(2, h2, scores_local, weight_scale, mode)
 
 

@@ -211,24 +211,29 @@ def nnz_balanced_ranges(row_ptr: torch.Tensor, parts: int, align: int = 32):
     return bounds
 
 
-def cyclic_relabel(g: Graph, parts: int):
-    """Relabel vertex v -> (v % parts) * ceil(n / parts) + v // parts so that contiguous ranges of
-    the new ids hold every parts-th original vertex: equal-sized shards (one NCCL all-gather per
-    exchange instead of per-owner broadcasts) whose work is balanced statistically even when the
-    degree depends on the id (R-MAT).  Adjacency lists keep their order, only the names change,
-    so per-vertex results are bit-identical: scores_new[perm[v]] == scores_old[v].
-    Returns (relabelled graph on ceil(n/parts)*parts ids -- padding vertices are isolated, weight 1 --,
-    perm [n] int64)."""
-    n = g.n
-    per = (n + parts - 1) // parts
-    n_pad = per * parts
+def live_rows(row_ptr: torch.Tensor, bounds) -> list:
+    """Per shard: how many of its leading rows can be a neighbour of anybody, i.e. 1 + the local
+    index of its last vertex with a non-empty adjacency list (symmetric graphs: an isolated vertex
+    is nobody's neighbour, its 16-float row never has to leave the GPU that computes it).  After
+    balanced_relabel every shard is sorted by descending degree, so this prefix is exactly its
+    non-isolated vertices."""
+    deg = row_ptr[1:] - row_ptr[:-1]
+    out = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        nz = torch.nonzero(deg[a:b] > 0)
+        out.append(int(nz[-1].item()) + 1 if nz.numel() else 0)
+    return out
+
+
+def relabel(g: Graph, perm: torch.Tensor, n_new: int, name: str) -> Graph:
+    """Rename vertex v -> perm[v] (a one-to-one map into [0, n_new)); ids without a preimage become
+    isolated vertices of weight 1.  Adjacency lists keep their order, only the names change, so
+    per-vertex results are bit-identical: scores_new[perm[v]] == scores_old[v]."""
     dev = g.row_ptr.device
-    v = torch.arange(n, dtype=torch.int64, device=dev)
-    perm = (v % parts) * per + v // parts
     deg = g.row_ptr[1:] - g.row_ptr[:-1]
-    new_deg = torch.zeros(n_pad, dtype=torch.int64, device=dev)
+    new_deg = torch.zeros(n_new, dtype=torch.int64, device=dev)
     new_deg[perm] = deg
-    row_ptr = torch.zeros(n_pad + 1, dtype=torch.int64, device=dev)
+    row_ptr = torch.zeros(n_new + 1, dtype=torch.int64, device=dev)
     row_ptr[1:] = torch.cumsum(new_deg, 0)
     # move every adjacency list to its new place, ids renamed, order kept
     src_new = torch.repeat_interleave(perm, deg)                    # new owner of every entry (old entry order)
@@ -237,9 +242,39 @@ def cyclic_relabel(g: Graph, parts: int):
     col_old = g.col.to(torch.int64) & 0xFFFFFFFF
     col = torch.empty(g.nnz, dtype=torch.int32, device=dev)
     col[dst] = to_u32(perm[col_old])
-    weights = torch.ones(n_pad, dtype=torch.int32, device=dev)
+    weights = torch.ones(n_new, dtype=torch.int32, device=dev)
     weights[perm] = g.weights
-    nw = torch.zeros(n_pad, dtype=torch.int32, device=dev)
+    nw = torch.zeros(n_new, dtype=torch.int32, device=dev)
     nw[perm] = g.nw
-    out = Graph(n=n_pad, row_ptr=row_ptr, col=col, weights=weights, nw=nw, name=g.name + f"_cyc{parts}")
-    return out, perm
+    return Graph(n=n_new, row_ptr=row_ptr, col=col, weights=weights, nw=nw, name=name)
+
+
+def cyclic_relabel(g: Graph, parts: int):
+    """Relabel vertex v -> (v % parts) * ceil(n / parts) + v // parts so that contiguous ranges of
+    the new ids hold every parts-th original vertex: equal-sized shards (one NCCL all-gather per
+    exchange instead of per-owner broadcasts).  Balances the WORK only when the degree does not
+    depend on the low bits of the id -- on R-MAT it does (see balanced_relabel).
+    Returns (relabelled graph on ceil(n/parts)*parts ids -- padding vertices are isolated, weight 1 --,
+    perm [n] int64)."""
+    n = g.n
+    per = (n + parts - 1) // parts
+    v = torch.arange(n, dtype=torch.int64, device=g.row_ptr.device)
+    perm = (v % parts) * per + v // parts
+    return relabel(g, perm, per * parts, g.name + f"_cyc{parts}"), perm
+
+
+def balanced_relabel(g: Graph, parts: int):
+    """Equal-sized shards with equal work: the vertices are dealt to the shards in order of
+    descending degree (the i-th largest goes to shard i % parts, slot i // parts), so every shard
+    gets the same number of vertices, the same number of adjacency entries up to one maximum
+    degree, and its share of the hubs.  An R-MAT id with zero low bits has several times the
+    expected degree, which is why dealing by id (cyclic_relabel) leaves shard 0 with about half of
+    all entries.  Same return value and bit-identity property as cyclic_relabel."""
+    n = g.n
+    per = (n + parts - 1) // parts
+    deg = g.row_ptr[1:] - g.row_ptr[:-1]
+    by_degree = torch.argsort(deg, descending=True, stable=True)
+    i = torch.arange(n, dtype=torch.int64, device=g.row_ptr.device)
+    perm = torch.empty(n, dtype=torch.int64, device=g.row_ptr.device)
+    perm[by_degree] = (i % parts) * per + i // parts
+    return relabel(g, perm, per * parts, g.name + f"_bal{parts}"), perm

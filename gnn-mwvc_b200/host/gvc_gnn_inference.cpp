@@ -33,27 +33,24 @@ namespace {
 const float *cdata(const matrix &m) { return m.get_height() * m.get_width() ? &m(0, 0) : nullptr; }
 float *mdata(matrix &m) { return m.get_height() * m.get_width() ? &m(0, 0) : nullptr; }
 
-// Host-side CSR scratch, reused between predict calls (the graph shrinks).
-struct csr_scratch {
-    std::vector<uint64_t> row_ptr;
-    std::vector<uint32_t> col, w, nw;
+// CSR view of the graph in the context's pinned staging buffers (gvc_graph_staging): the
+// extraction writes where the DMA reads, there is no second host copy.
+struct csr_view {
+    uint64_t *row_ptr = nullptr;
+    uint32_t *col = nullptr, *w = nullptr, *nw = nullptr;
+    uint64_t nnz = 0;
 };
-
-csr_scratch &scratch() {
-    static csr_scratch s;
-    return s;
-}
 
 // What predict reads from the graph: size(), begin(u)/end(u), W(u), NW(u)
 // (reference src/gnn_inference.cpp:32-40).  D(u) is end(u)-begin(u): calling g.D(u)
 // would write the graph's mutable cursor (include/reduction_graph.hpp:144,240-245).
 // The ranges have holes and the raw edge array is much longer than the live
 // adjacency, so rows are compacted here, never uploaded raw.
-void extract_csr(const reduction_graph<Tn, Tw> &g, csr_scratch &s) {
+csr_view extract_csr(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g) {
     const Tn n = g.size();
-    s.row_ptr.resize((size_t)n + 1);
-    s.w.resize(n);
-    s.nw.resize(n);
+    csr_view s;
+    int rc = gvc_graph_staging(ctx, n, 0, &s.row_ptr, &s.col, &s.w, &s.nw);
+    if (rc != 0) gvc_host::die("gvc_graph_staging", rc);
     // begin(u)/end(u)/W(u)/NW(u) only read the graph, so vertex ranges can be walked by several
     // threads (never D(u) / operator[], which write a cursor)
     const unsigned hw = std::thread::hardware_concurrency();
@@ -77,10 +74,14 @@ void extract_csr(const reduction_graph<Tn, Tw> &g, csr_scratch &s) {
     });
     s.row_ptr[0] = 0;
     for (Tn u = 0; u < n; ++u) s.row_ptr[u + 1] += s.row_ptr[u];
-    s.col.resize(s.row_ptr[n]);
+    s.nnz = s.row_ptr[n];
+    // now that nnz is known: the adjacency buffer (the per-vertex ones are big enough and stay)
+    rc = gvc_graph_staging(ctx, n, s.nnz, &s.row_ptr, &s.col, &s.w, &s.nw);
+    if (rc != 0) gvc_host::die("gvc_graph_staging", rc);
     for_ranges([&](Tn a, Tn b) {
-        for (Tn u = a; u < b; ++u) std::copy(g.begin(u), g.end(u), s.col.begin() + s.row_ptr[u]);
+        for (Tn u = a; u < b; ++u) std::copy(g.begin(u), g.end(u), s.col + s.row_ptr[u]);
     });
+    return s;
 }
 
 // GVC_PROFILE=1: per-call and cumulative timing of predict() on stderr (CSR extraction on the
@@ -188,9 +189,8 @@ void graph_layer::forward(const matrix &in, matrix &out, const reduction_graph<T
     out.resize(n, 2 * w + 3);
     if (n == 0) return;
     gvc_ctx *ctx = gvc_host::context();
-    csr_scratch &s = scratch();
-    extract_csr(g, s);
-    int rc = gvc_graph_upload(ctx, g.size(), s.row_ptr.data(), s.col.data(), s.w.data(), s.nw.data());
+    const csr_view s = extract_csr(ctx, g);
+    int rc = gvc_graph_upload(ctx, g.size(), s.row_ptr, s.col, s.w, s.nw);
     if (rc != 0) gvc_host::die("gvc_graph_upload", rc);
     rc = gvc_graph_layer_host(ctx, cdata(in), (int)w, mdata(out), WEIGHT_SCALE);
     if (rc != 0) gvc_host::die("gvc_graph_layer_host", rc);
@@ -238,10 +238,9 @@ void model::predict(const matrix &in, matrix &out, const reduction_graph<Tn, Tw>
 
     predict_profile &pf = profile();
     const double t0 = now_s();
-    csr_scratch &s = scratch();
-    extract_csr(g, s);
+    const csr_view s = extract_csr(ctx, g);
     const double t1 = now_s();
-    int rc = gvc_graph_upload(ctx, n, s.row_ptr.data(), s.col.data(), s.w.data(), s.nw.data());
+    int rc = gvc_graph_upload(ctx, n, s.row_ptr, s.col, s.w, s.nw);
     if (rc != 0) gvc_host::die("gvc_graph_upload", rc);
     const double t2 = now_s();
     rc = gvc_forward(ctx, cdata(in), scale, mdata(out), gvc_host::mode());
@@ -250,7 +249,7 @@ void model::predict(const matrix &in, matrix &out, const reduction_graph<Tn, Tw>
     pf.calls++; pf.extract += t1 - t0; pf.upload += t2 - t1; pf.forward += t3 - t2;
     if (pf.on)
         std::fprintf(stderr, "gvc profile: predict n=%u nnz=%zu extract %.2f ms upload %.2f ms forward %.2f ms\n", n,
-                     s.col.size(), 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2));
+                     (size_t)s.nnz, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2));
 }
 
 // ---- text format (src/gnn_inference.cpp:92-139) --------------------------------

@@ -82,7 +82,9 @@ int gvc_model_is_fused(const gvc_ctx *ctx);
  *
  * CSR with n vertices: row_ptr[n+1] (row_ptr[0] == 0), col[row_ptr[n]]
  * 0-indexed neighbour ids in the order begin(u)..end(u) yields them, W[n] and
- * NW[n] the integer vertex and neighbourhood weights.  Host pointers, copied. */
+ * NW[n] the integer vertex and neighbourhood weights.  Host pointers, copied.
+ * Checked on the device during the upload: row_ptr monotone, every neighbour id
+ * < n (GVC_ERR_ARG otherwise, and the context is left without a graph). */
 int gvc_graph_upload(gvc_ctx *ctx, uint32_t n, const uint64_t *row_ptr, const uint32_t *col,
                      const uint32_t *W, const uint32_t *NW);
 
@@ -93,6 +95,17 @@ int gvc_graph_upload(gvc_ctx *ctx, uint32_t n, const uint64_t *row_ptr, const ui
 int gvc_graph_upload_shard(gvc_ctx *ctx, uint32_t n_global, uint32_t v_begin, uint32_t v_end,
                            const uint64_t *row_ptr, const uint32_t *col, const uint32_t *W,
                            const uint32_t *NW);
+
+/* Pinned host buffers owned by the context, big enough for a shard of n_local vertices and nnz
+ * adjacency entries: row_ptr[n_local + 1], col[nnz], W[n_local], NW[n_local].  A caller that
+ * builds its CSR anyway (the drop-in's extraction from the reduction_graph,
+ * gnn-mwvc_b200/host/gvc_gnn_inference.cpp) writes it here and passes these pointers to
+ * gvc_graph_upload[_shard]: the copies then run as DMA straight from the buffers, the adjacency
+ * on a second stream beside the schedule construction.  Any other host pointers stay valid
+ * arguments of the upload calls, just slower.  The buffers are valid until the next
+ * gvc_graph_staging call with larger sizes or gvc_ctx_destroy. */
+int gvc_graph_staging(gvc_ctx *ctx, uint32_t n_local, uint64_t nnz, uint64_t **row_ptr,
+                      uint32_t **col, uint32_t **W, uint32_t **NW);
 
 /* Same shard description with DEVICE pointers that stay owned by the caller and
  * must outlive the context's use of them (no copy; row_ptr is uint32 here, the
@@ -105,7 +118,7 @@ int gvc_graph_adopt_device(gvc_ctx *ctx, uint32_t n_global, uint32_t v_begin, ui
 /* Exact mode reproduces OpenBLAS' 1-row remainder kernel for the LAST vertex of a graph with an
  * odd vertex count (oracle/gnn_oracle.c).  By default that is vertex n_global - 1 and it is
  * handled by the shard that owns it.  A caller that renames vertices before sharding
- * (gnn-mwvc_b200/graphs.py cyclic_relabel) says where that vertex went: has_tail = 0 -> this
+ * (gnn-mwvc_b200/graphs.py balanced_relabel) says where that vertex went: has_tail = 0 -> this
  * shard owns no such vertex, 1 -> it is local vertex `local_index`.  Call after the graph
  * upload/adopt (which resets to the default). */
 int gvc_graph_set_tail(gvc_ctx *ctx, int has_tail, uint32_t local_index);

@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, layout):
     import sys
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "tests"))
@@ -38,9 +38,18 @@ def _worker(rank, world, port, ret):
     layers = capi.load_model_npz(GOLDEN / "mwvc_model.npz")
     orc = po.Oracle()
     g = graphs.rmat_graph(11, 12, seed=5, n_limit=1777)
-    rp, col, W, NW, x, s = inputs_of(g)
-    bounds = graphs.nnz_balanced_ranges(g.row_ptr, world)
-    shard = gdist.make_shard(g, bounds, rank)
+    if layout == "balanced":
+        # the benchmark's layout: equal shards dealt by descending degree, rows of isolated
+        # vertices stay home
+        g0, (rp0, col0, W0, NW0, x0, s0) = g, inputs_of(g)
+        g, perm = graphs.balanced_relabel(g0, world)
+        per = g.n // world
+        bounds = [r * per for r in range(world + 1)]
+    else:
+        s0 = None
+        bounds = graphs.nnz_balanced_ranges(g.row_ptr, world)
+    rp, col, W, NW, x, s = inputs_of(g, s0)
+    shard = gdist.make_shard(g, bounds, rank, skip_isolated=(layout == "balanced"))
     a, b = shard.v_begin, shard.v_end
     assert shard.row_ptr[0] == 0 and shard.nnz == int(rp[b] - rp[a])
     assert np.array_equal(shard.col.numpy().view(np.uint32), col[int(rp[a]):int(rp[b])])
@@ -77,10 +86,23 @@ def _worker(rank, world, port, ret):
     scores = torch.empty(b - a)
     gdist.sharded_forward(stage_fn, shard, x_full, h1, h2, scores, s, 0)
     full = gdist.gather_scores(scores, bounds)
-    assert not torch.isnan(h1).any() and not torch.isnan(h2).any()     # every row arrived everywhere
+    if layout == "balanced":
+        deg = np.diff(rp.astype(np.int64))
+        missing = torch.isnan(h1).any(1).numpy()
+        assert not missing[deg > 0].any()                  # every row somebody can read arrived
+        assert not missing[a:b].any()
+        assert missing.sum() > 0                           # and rows of remote isolated vertices did not travel
+        assert len(set(shard.live)) >= 1 and max(shard.live) < per
+    else:
+        assert not torch.isnan(h1).any() and not torch.isnan(h2).any()     # every row arrived everywhere
     if rank == 0:
-        want = orc.predict(orc.parse(po.layers_to_text(layers)), rp, col, W, NW, x, s)[:, 0]
-        ret["equal"] = bool(np.array_equal(full.numpy().view(np.uint32), want.view(np.uint32)))
+        if layout == "balanced":
+            want = orc.predict(orc.parse(po.layers_to_text(layers)), rp0, col0, W0, NW0, x0, s)[:, 0]
+            got = full.numpy()[perm.numpy()]
+        else:
+            want = orc.predict(orc.parse(po.layers_to_text(layers)), rp, col, W, NW, x, s)[:, 0]
+            got = full.numpy()
+        ret["equal"] = bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))
         ret["bounds"] = bounds
     dist.barrier()
     dist.destroy_process_group()
@@ -90,10 +112,17 @@ def _worker(rank, world, port, ret):
 def test_sharded_forward_over_gloo(world):
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), ret, "ranges"), nprocs=world, join=True)
     assert ret["equal"]
     b = ret["bounds"]
     assert b[0] == 0 and len(b) == world + 1 and len(set(np.diff(b))) > 1   # unequal slices were exchanged
+
+
+def test_balanced_shards_skip_isolated_rows_over_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret, "balanced"), nprocs=2, join=True)
+    assert ret["equal"]
 
 
 def test_shard_cut_is_a_partition():

@@ -206,6 +206,44 @@ def test_shards_are_bit_identical_to_one_gpu(ctx, model_layers):
             c.close()
 
 
+def test_relabelled_shards_are_bit_identical(ctx, model_layers):
+    """The benchmark's multi-GPU layout: vertices dealt to equal shards by descending degree
+    (graphs.balanced_relabel), odd vertex count so the exact-mode tail vertex moves too."""
+    g0 = graphs.rmat_graph(13, 16, seed=62, n_limit=8189)
+    rp0, col0, W0, NW0, x0, s = inputs_of(g0)
+    ctx.graph_upload(rp0, col0, W0, NW0)
+    want = ctx.forward(x0, s)
+    dev = torch.device("cuda:0")
+    for parts in (2, 4):
+        g, perm = graphs.balanced_relabel(g0, parts)
+        rp, col, W, NW, x, _ = inputs_of(g, s)
+        per = g.n // parts
+        tail = int(perm[g0.n - 1])
+        shards = []
+        for p in range(parts):
+            a, b = p * per, (p + 1) * per
+            c = pkg.Context(0)
+            c.model_upload(model_layers)
+            lo, hi = int(rp[a]), int(rp[b])
+            c.graph_upload(rp[a:b + 1] - rp[a], col[lo:hi], W[a:b], NW[a:b], n_global=g.n, v_begin=a, v_end=b)
+            c.graph_set_tail(tail)
+            shards.append(c)
+        dx = torch.from_numpy(x).to(dev)
+        d1 = torch.zeros(g.n, 16, device=dev)
+        d2 = torch.zeros(g.n, 16, device=dev)
+        out = torch.empty(g.n, device=dev)
+        torch.cuda.synchronize()
+        for stage, (src, dst) in enumerate(((dx, d1), (d1, d2), (d2, None))):
+            for p, c in enumerate(shards):
+                c.stage_device(stage, src, dst if dst is not None else out[p * per:(p + 1) * per], s)
+            for c in shards:
+                c.sync()
+        got = out.cpu().numpy()[perm.numpy()]
+        assert_bit_equal(got, want, f"{parts} relabelled shards")
+        for c in shards:
+            c.close()
+
+
 def test_generic_path_any_layer_sequence(oracle):
     """operator>> accepts any sequence of the four layer kinds; non-GNN_VC models run on
     the per-layer kernels (SURVEY.md 8(b) genericity)."""
@@ -248,6 +286,33 @@ def test_single_layers_vs_golden(ctx, vec, lay):
     np.testing.assert_allclose(ctx.sgemm_host(A, B), A @ B, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(ctx.sgemm_host(A.T.copy(), B, trans_a=True), A @ B, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(ctx.sgemm_host(A, B.T.copy(), trans_b=True), A @ B, rtol=1e-5, atol=1e-6)
+
+
+def test_upload_from_pinned_staging(ctx, oracle, oracle_model):
+    """The drop-in's way in: CSR written into the context's pinned buffers, uploaded by DMA."""
+    for g in (graphs.rmat_graph(12, 8, seed=9), graphs.er_graph(1001, 4000, seed=2)):
+        rp, col, W, NW, x, s = inputs_of(g)
+        want = oracle.predict(oracle_model, rp, col, W, NW, x, s)[:, 0]
+        for _ in range(2):                                   # second round reuses the buffers
+            srp, scol, sW, sNW = ctx.graph_staging(g.n, len(col))
+            srp[:], scol[:], sW[:], sNW[:] = rp, col, W, NW
+            ctx.graph_upload(srp, scol, sW, sNW)
+            assert_bit_equal(ctx.forward(x, s), want, g.name)
+
+
+def test_upload_rejects_broken_csr(ctx, vec):
+    g, s, want = golden_graph(vec, "er607")
+    rp, col, W, NW, x, _ = inputs_of(g, s)
+    bad = col.copy(); bad[len(bad) // 2] = g.n                # an id one past the last vertex
+    with pytest.raises(capi.GvcError, match="neighbour id"):
+        ctx.graph_upload(rp, bad, W, NW)
+    with pytest.raises(capi.GvcError, match="no graph"):
+        ctx.forward_device(0, s, 0)                           # the rejected graph is not left behind
+    bad = rp.copy(); bad[5], bad[6] = bad[6] + 1, bad[5]       # offsets going backwards
+    with pytest.raises(capi.GvcError, match="row_ptr"):
+        ctx.graph_upload(bad, col, W, NW)
+    ctx.graph_upload(rp, col, W, NW)                          # the context is still good
+    assert_bit_equal(ctx.forward(x, s), want, "after rejected uploads")
 
 
 def test_errors_are_reported_not_fatal(ctx):

@@ -2,6 +2,7 @@
 import hashlib
 
 import numpy as np
+import pytest
 import torch
 
 import gnn_mwvc_b200  # noqa: F401
@@ -64,6 +65,31 @@ def test_nnz_balanced_ranges():
         nnz = [int(g.row_ptr[b[i + 1]] - g.row_ptr[b[i]]) for i in range(parts)]
         cost = [nnz[i] + 16 * (b[i + 1] - b[i]) for i in range(parts)]
         assert max(cost) < 1.35 * (sum(cost) / parts)
+
+
+@pytest.mark.parametrize("fn", ["cyclic_relabel", "balanced_relabel"])
+def test_relabel_keeps_lists_and_balances(fn):
+    g = graphs.rmat_graph(12, 16, seed=5, n_limit=4093)
+    parts = 4
+    h, perm = getattr(graphs, fn)(g, parts)
+    per = -(-g.n // parts)
+    assert h.n == per * parts and h.nnz == g.nnz
+    assert torch.equal(torch.sort(perm).values.unique(), torch.sort(perm).values)        # one-to-one
+    rp, col = g.row_ptr.numpy(), g.col.numpy().view(np.uint32)
+    hrp, hcol = h.row_ptr.numpy(), h.col.numpy().view(np.uint32)
+    pm = perm.numpy()
+    for v in (0, 1, 17, g.n - 1, int(np.argmax(np.diff(rp)))):                          # lists: same order, new names
+        want = pm[col[rp[v]:rp[v + 1]]]
+        got = hcol[hrp[pm[v]]:hrp[pm[v] + 1]]
+        assert np.array_equal(got, want)
+        assert h.weights[pm[v]] == g.weights[v] and h.nw[pm[v]] == g.nw[v]
+    pad = np.setdiff1d(np.arange(h.n), pm)
+    assert all(hrp[p + 1] == hrp[p] for p in pad)                                       # padding is isolated
+    shard_nnz = [int(hrp[(r + 1) * per] - hrp[r * per]) for r in range(parts)]
+    if fn == "balanced_relabel":
+        assert max(shard_nnz) - min(shard_nnz) <= int(np.diff(rp).max())                # equal work up to one hub
+    else:
+        assert max(shard_nnz) > 1.5 * min(shard_nnz)      # R-MAT: ids with zero low bits are the heavy ones
 
 
 def test_u32_bit_patterns():

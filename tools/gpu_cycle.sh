@@ -10,7 +10,7 @@ import json
 for f in ("gpurun_out/bench_${tag}.json","gpurun_out/bench_${tag}_fast.json"):
     try:
         d=json.load(open(f)); r=d["roofline"]
-        print(f, "ms/step %.3f"%d["ms_per_step"], "Gedges/s %.2f"%(d["value"]/1e9), "stage_ms", [round(x,3) for x in r["stage_ms"]], "fwd_frac %.3f"%r["forward_frac"], "e2e ms %.3f"%d["e2e"]["ms_per_step"], d["clocks"])
+        print(f, "ms/step %.3f"%d["ms_per_step"], "Gedges/s %.2f"%(d["value"]/1e9), "stage_ms", [round(x,3) for x in r["stage_ms"]], "fwd_frac %.3f"%r["forward_frac"], "e2e ms %.3f (upload %.3f, %.1f GB/s; resident %.3f)"%(d["e2e"]["ms_per_step"], d["e2e"]["graph_upload_ms"], d["e2e"]["graph_upload_GBps"], d["e2e"]["csr_resident"]["ms_per_step"]), d["clocks"])
     except Exception as e: print(f, "FAILED", e)
 PY
 if [ "$2" = "ncu" ]; then

@@ -29,7 +29,7 @@ def main():
     g = graphs.rmat_graph(scale_log2, 16, seed=7, device=dev, n_limit=(1 << scale_log2) - 3)   # odd vertex count
     s = 200.0
     x = (g.weights.to(torch.float32) / s).contiguous()
-    for layout in ("ranges", "cyclic"):
+    for layout in ("ranges", "balanced"):
         run_layout(layout, g, x, s, layers, rank, world, local, dev)
     if rank == 0:
         print(f"MULTI_GPU_PARITY ok world={world} n={g.n} E={g.n_edges}", flush=True)
@@ -39,9 +39,9 @@ def main():
 
 def run_layout(layout, g0, x0, s, layers, rank, world, local, dev):
     """ranges: work-balanced contiguous ranges of the original ids (unequal, per-owner broadcasts);
-    cyclic: equal ranges of the cyclically relabelled graph (one all-gather per exchange)."""
-    if layout == "cyclic":
-        g, perm = graphs.cyclic_relabel(g0, world)
+    balanced: equal ranges of the degree-dealt relabelled graph (one all-gather per exchange)."""
+    if layout == "balanced":
+        g, perm = graphs.balanced_relabel(g0, world)
         x = (g.weights.to(torch.float32) / s).contiguous()
         per = g.n // world
         bounds = [r * per for r in range(world + 1)]
@@ -50,7 +50,7 @@ def run_layout(layout, g0, x0, s, layers, rank, world, local, dev):
         g, perm, x = g0, None, x0
         bounds = graphs.nnz_balanced_ranges(g.row_ptr, world)
         tail = "default"
-    shard = gdist.make_shard(g, bounds, rank)
+    shard = gdist.make_shard(g, bounds, rank, skip_isolated=(layout == "balanced"))
     for mode in (pkg.MODE_EXACT, pkg.MODE_FAST):
         ctx = pkg.Context(local)
         ctx.model_upload(layers)

@@ -130,6 +130,11 @@ struct gvc_ctx {
     DevBuf<uint32_t> d_order, d_bins, d_sync;
     DevBuf<uint4> d_vrec;
     DevBuf<float> d_feat;
+    // fast-mode hub chunks (gvc::HubSplit): [0] the ring vertices (width 16), [1] the stage-0 giants
+    DevBuf<uint4> d_hub_chunk[2];
+    DevBuf<uint2> d_hub_info[2];
+    DevBuf<float> d_hub_partial[2];
+    DevBuf<uint32_t> d_hub_count;
     gvc::Schedule sched{};
     int num_sms = 148;
     int ctas_per_sm[3] = {1, 1, 1};      // resident CTAs per SM of each stage kernel (occupancy query)
@@ -282,9 +287,11 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     const uint32_t nl = c->n_local();
     if (nl == 0) return 0;
     const Schedule &sc = c->sched;
-    const uint32_t n_tasks = STAGE == 0 ? sc.n_giant1 + (nl - sc.n_giant1 + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
+    const bool exact = mode == GVC_MODE_EXACT;
+    const uint32_t n_tasks = STAGE == 0 ? (exact ? sc.n_giant1 : sc.n_chunks1) + (nl - sc.n_giant1 + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
                                         : (sc.n_mid + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
-    const unsigned want = std::max<unsigned>(STAGE == 0 ? 0u : sc.n_ring, (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
+    const unsigned want = std::max<unsigned>(STAGE == 0 ? 0u : (exact ? sc.n_ring : sc.n_chunks16),
+                                             (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
     // persistent kernel: never more CTAs than can be resident at once (warps wait on each other's
     // feature vectors; a CTA that is not running could never deliver its ring tasks)
     const unsigned grid = std::max(1u, std::min<unsigned>(c->ctas_per_sm[STAGE] * c->num_sms, want));
@@ -292,14 +299,18 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     sc_launch.n_ring_ctas = std::min<unsigned>(grid, (unsigned)c->num_sms);   // one ring CTA per SM at most
     const size_t smem = stage_smem_bytes<STAGE>();
     // task counter + per-feature-tile completion counters start at zero
-    GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (kSyncCounters + (size_t)sc.n_feat_tiles) * sizeof(uint32_t), c->stream));
+    const int hk = STAGE == 0 ? 1 : 0;
+    const uint32_t n_split = STAGE == 0 ? sc.n_giant1 : sc.n_ring;
+    HubSplit hub{c->d_hub_chunk[hk].p, c->d_hub_info[hk].p, c->d_hub_partial[hk].p,
+                 c->d_sync.p + kSyncCounters + sc.n_feat_tiles};
+    GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (kSyncCounters + (size_t)sc.n_feat_tiles + (exact ? 0 : n_split)) * sizeof(uint32_t), c->stream));
     if (mode == GVC_MODE_EXACT) {
         stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, hub, c->d_feat.p, c->d_sync.p, d_in, d_out,
             c->d_stage_params[STAGE], c->v_begin, scale);
     } else {
         stage_kernel<STAGE, false><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, hub, c->d_feat.p, c->d_sync.p, d_in, d_out,
             c->d_stage_params[STAGE], c->v_begin, scale);
     }
     GVC_CUDA(cudaGetLastError());
@@ -380,12 +391,32 @@ int build_schedule(gvc_ctx *c) {
     sc.n_tiles = (nl - n_pre + kTileVerts - 1) / kTileVerts;
     sc.n_feat_tiles = (n_pre + kTileVerts - 1) / kTileVerts;
     if ((rc = c->d_feat.reserve((size_t)n_pre * 32))) return rc;
-    if ((rc = c->d_sync.reserve(kSyncCounters + (size_t)sc.n_feat_tiles))) return rc;
+    // counters: task claims, feature tiles, then one "chunks done" counter per split vertex
+    if ((rc = c->d_sync.reserve(kSyncCounters + (size_t)sc.n_feat_tiles + std::max(n_ring, n_giant1)))) return rc;
     GVC_CUDA(cudaMemcpyAsync(c->d_bins.p, start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
     degree_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, c->Wv, nl, c->d_bins.p, c->d_order.p, c->d_vrec.p);
     GVC_CUDA(cudaGetLastError());
     c->launches++;
-    GVC_CUDA(cudaStreamSynchronize(c->stream));   // `start` lives on this stack frame
+    // fast-mode chunk lists of the two hub classes
+    const uint32_t n_class[2] = {n_ring, n_giant1}, chunk_len[2] = {kChunk16, kChunk1};
+    uint32_t n_chunks[2] = {0, 0};
+    if ((rc = c->d_hub_count.reserve(2))) return rc;
+    GVC_CUDA(cudaMemsetAsync(c->d_hub_count.p, 0, 2 * sizeof(uint32_t), c->stream));
+    for (int k = 0; k < 2; ++k) {
+        if (!n_class[k]) continue;
+        const size_t bound = (size_t)(c->nnz / chunk_len[k]) + n_class[k];
+        if ((rc = c->d_hub_chunk[k].reserve(bound))) return rc;
+        if ((rc = c->d_hub_info[k].reserve(n_class[k]))) return rc;
+        if ((rc = c->d_hub_partial[k].reserve(bound * (k == 0 ? 16 : 1)))) return rc;
+        hub_chunks_kernel<<<std::min<unsigned>(1184, (n_class[k] + 255) / 256), 256, 0, c->stream>>>(
+            c->d_vrec.p, n_class[k], chunk_len[k], c->d_hub_count.p + k, c->d_hub_info[k].p, c->d_hub_chunk[k].p);
+        GVC_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    GVC_CUDA(cudaMemcpyAsync(n_chunks, c->d_hub_count.p, sizeof(n_chunks), cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));   // `start` and `n_chunks` live on this stack frame
+    sc.n_chunks16 = n_chunks[0];
+    sc.n_chunks1 = n_chunks[1];
     return 0;
 }
 
@@ -542,6 +573,8 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     c->d_row_ptr64.release(); c->d_flag.release();
     c->stg_row_ptr.release(); c->stg_col.release(); c->stg_W.release(); c->stg_NW.release();
     c->d_order.release(); c->d_vrec.release(); c->d_bins.release(); c->d_sync.release(); c->d_feat.release();
+    for (int k = 0; k < 2; ++k) { c->d_hub_chunk[k].release(); c->d_hub_info[k].release(); c->d_hub_partial[k].release(); }
+    c->d_hub_count.release();
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
     c->d_ping.release(); c->d_pong.release();
     c->pin_x.release(); c->pin_scores.release();

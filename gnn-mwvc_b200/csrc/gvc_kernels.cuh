@@ -96,6 +96,29 @@ struct Schedule {
     uint32_t n_giant1;      // order[0, n_giant1): deg >= kGiant1MinDeg, the single-warp tasks of stage 0 (w = 1)
     uint32_t n_tiles;       // 32-vertex tiles over order[n_ring + n_mid, n_local)
     uint32_t n_feat_tiles;  // 32-vertex feature tiles over order[0, n_ring + n_mid)
+    uint32_t n_chunks16;    // fast mode: chunks the ring vertices are cut into (HubSplit), width 16
+    uint32_t n_chunks1;     // fast mode: chunks of the stage-0 giants
+};
+
+// Fast mode owes the reference no summation order, so one huge vertex need not be one task: its
+// adjacency list is cut into chunks of kChunk16 (a CTA each, width 16) or kChunk1 (a warp each,
+// width 1) entries, every chunk leaves a partial sum in its slot, and whoever finishes the last
+// chunk of a vertex adds the slots up in chunk order (deterministic).  chunk[k] = {position g in
+// `order`, chunk index}; info[g] = {first slot, number of chunks}; done[g] counts finished chunks
+// (zeroed with the other counters before every launch).
+#ifndef GVC_CHUNK16
+#define GVC_CHUNK16 4096
+#endif
+#ifndef GVC_CHUNK1
+#define GVC_CHUNK1 4096
+#endif
+constexpr uint32_t kChunk16 = GVC_CHUNK16;
+constexpr uint32_t kChunk1 = GVC_CHUNK1;
+struct HubSplit {
+    const uint4 *chunk;
+    const uint2 *info;
+    float *partial;
+    uint32_t *done;
 };
 
 // degree -> bin, monotone in the degree, 4 bins per octave
@@ -558,11 +581,33 @@ __device__ __forceinline__ float chain_add16(const float *__restrict__ S, int cn
     return acc;
 }
 
+// the same chain over a full batch of 64 rows whose first 8 values are already in registers
+// (loaded before the running sum arrived)
+__device__ __forceinline__ float chain_add16_full(const float *__restrict__ S, float (&va)[8], float acc, int lane) {
+    const float *s = S + (lane & 15);
+    float vb[8];
+#pragma unroll
+    for (int g = 0; g < 8; g += 2) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) vb[t] = s[((g + 1) * 8 + t) * 16];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, va[t]);
+        if (g + 2 < 8) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) va[t] = s[((g + 2) * 8 + t) * 16];
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, vb[t]);
+    }
+    return acc;
+}
+
 // ring task, width 16: the 8 warps of the CTA serve one vertex.  Warp w fetches batches
 // w, w+8, ... (64 rows each) into its own tile buffer; the running sum travels from warp
 // to warp through shared memory, the hand-over for batch b is named barrier 1 + b % 8
-// (arrive by the warp that summed b-1, sync by the warp that sums b).  All 8 warps call
-// this; the caller reads the 16 sums from ring_acc after a __syncthreads().
+// (arrive by the warp that summed b-1, sync by the warp that sums b; polling a {value, sequence
+// number} slot instead of the barrier was measured slower: 4.5 vs 3.9 ns per neighbour).  All 8
+// warps call this; the caller reads the 16 sums from ring_acc after a __syncthreads().
 __device__ __noinline__ void ring_gather16_exact(float *__restrict__ S, float *__restrict__ ring_acc,
                                               const uint32_t *__restrict__ col,
                                               const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
@@ -587,12 +632,18 @@ __device__ __noinline__ void ring_gather16_exact(float *__restrict__ S, float *_
         ids = coop_load_ids(col, e0 + 3 * kStep, end_of(b + 3 * kWarpsPerCta), lane);
         coop_stage_rows16(S, r, lane);
         __syncwarp();
+        const int cnt = (int)min(64u, end - e0);
+        float va[8];
+        if (cnt == 64) {                       // first values of the batch: on hand before the sum arrives
+#pragma unroll
+            for (int t = 0; t < 8; ++t) va[t] = S[t * 16 + (lane & 15)];
+        }
         float acc = 0.0f;
         if (b > 0) {
             named_bar_sync(1 + (int)(b % kWarpsPerCta), 64);
             acc = ring_acc[lane & 15];
         }
-        acc = chain_add16(S, (int)min(64u, end - e0), acc, lane);
+        acc = cnt == 64 ? chain_add16_full(S, va, acc, lane) : chain_add16(S, cnt, acc, lane);
         __syncwarp();
         if (lane < 16) ring_acc[lane] = acc;
         if (b + 1 < nb) named_bar_arrive(1 + (int)((b + 1) % kWarpsPerCta), 64);
@@ -642,7 +693,9 @@ __device__ __noinline__ void ring_gather16_fast(float *__restrict__ part, const 
 // FADD), about 0.5 us per block, a gather under load takes several times that: the values of the
 // next kGiant1Depth blocks and the ids of two blocks beyond those are in flight while a block is
 // summed.  The block is parked in shared memory and every lane walks it with broadcast 128-bit
-// loads.
+// loads.  Measured alternatives, both slower (3.4 ns per neighbour here): cp.async of the single
+// values straight into a shared-memory ring (4.4 ns), and the prefetch code placed behind the
+// fully unrolled chain's first loads so that the scheduler can interleave them (3.95 ns).
 constexpr int kGiant1Depth = 4;
 
 __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 floats */,
@@ -681,10 +734,20 @@ __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 float
 #pragma unroll
             for (int t = 0; t < 8; ++t) v[k][t] = v[k + 1][t];
         }
-        ld_x(v[K - 1], ida, blk + K);             // values K blocks ahead
+        if (blk + K + 4 <= nb) {
+            // blocks blk + K and blk + K + 2 are full: no bounds checks, one base address per block
+            // (every instruction spent on fetching is time the chain of this single warp stands still)
 #pragma unroll
-        for (int t = 0; t < 8; ++t) ida[t] = idb[t];
-        ld_ids(idb, blk + K + 2);
+            for (int t = 0; t < 8; ++t) v[K - 1][t] = __ldg(x + ida[t]);
+            const uint32_t *cp = col + e0 + 256 * (K + 2) + lane;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { ida[t] = idb[t]; idb[t] = ld_id(cp + 32 * t); }
+        } else {
+            ld_x(v[K - 1], ida, blk + K);         // values K blocks ahead
+#pragma unroll
+            for (int t = 0; t < 8; ++t) ida[t] = idb[t];
+            ld_ids(idb, blk + K + 2);
+        }
         __syncwarp();
         const int cnt = (int)min(256u, end - e0);
         const float4 *s4 = reinterpret_cast<const float4 *>(S);
@@ -717,17 +780,36 @@ __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 float
     return acc;
 }
 
-// fast mode: every lane sums its own elements, one shuffle reduction at the end
+// fast mode: every lane sums its own elements, one shuffle reduction at the end; the values of
+// the next block and the ids of the one after are in flight while a block is added up
 __device__ __noinline__ float coop_gather1_fast(const uint32_t *__restrict__ col, const float *__restrict__ x,
                                                 uint32_t beg, uint32_t end, int lane) {
     float acc = 0.0f;
+    if (beg >= end) return acc;
+    const uint32_t nb = (end - beg + 255) / 256;
+    uint32_t id[8];
+    float v[8], vn[8];
+    auto ld_ids = [&](uint32_t blk) {
+        const uint32_t e0 = beg + 256 * blk, lim = blk < nb ? end : 0u;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < lim) ? ld_id(col + e) : 0u; }
+    };
+    auto ld_x = [&](float (&val)[8], uint32_t blk) {
+        const uint32_t e0 = beg + 256 * blk, lim = blk < nb ? end : 0u;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; val[t] = (e < lim) ? __ldg(x + id[t]) : 0.0f; }
+    };
+    ld_ids(0);
+    ld_x(v, 0);
+    ld_ids(1);
 #pragma unroll 1
-    for (uint32_t e0 = beg; e0 < end; e0 += 256) {
-        uint32_t id[8];
+    for (uint32_t blk = 0; blk < nb; ++blk) {
+        ld_x(vn, blk + 1);
+        ld_ids(blk + 2);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < end) ? ld_id(col + e) : 0u; }
+        for (int t = 0; t < 8; ++t) acc += v[t];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; acc += (e < end) ? __ldg(x + id[t]) : 0.0f; }
+        for (int t = 0; t < 8; ++t) v[t] = vn[t];
     }
 #pragma unroll
     for (int m = 1; m < 32; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
@@ -781,15 +863,15 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
              const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
              const uint32_t *__restrict__ order, const uint4 *__restrict__ vrec, const Schedule sc,
-             float *__restrict__ feat,
+             const HubSplit hub, float *__restrict__ feat,
              uint32_t *__restrict__ sync, const float *__restrict__ in, float *__restrict__ out,
              const float *__restrict__ params, uint32_t v_begin, float scale) {
     constexpr StageDims D = stage_dims(STAGE);
     extern __shared__ __align__(16) float smem[];
     float *P = smem;                                             // packed parameters
     constexpr int kParamFloats = (D.floats() + 3) / 4 * 4;
-    float *ring_acc = smem + kParamFloats;                       // 16 floats + the CTA's ring claim
-    float *warp_mem = ring_acc + 20;
+    float *ring_acc = smem + kParamFloats;                       // 16 sums, the CTA's ring claim [16], a chunk record [20..23]
+    float *warp_mem = ring_acc + 24;
 
     for (int i = threadIdx.x; i < D.floats(); i += kCtaThreads) P[i] = __ldg(params + i);
     __syncthreads();
@@ -805,31 +887,80 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     if constexpr (STAGE != 0) {
         // claimed one at a time, largest first: a CTA that drew a huge vertex takes fewer of them
         uint32_t *claim = reinterpret_cast<uint32_t *>(ring_acc) + 16;
+        if constexpr (EXACT) {
 #pragma unroll 1
-        while (blockIdx.x < sc.n_ring_ctas && sc.n_ring) {
-            if (threadIdx.x == 0) *claim = atomicAdd(sync + 3, 1u);
-            __syncthreads();
-            const uint32_t g = *claim;
-            if (g >= sc.n_ring) break;
-            const uint32_t ul = __ldg(order + g);
-            const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-            if constexpr (EXACT) {
+            while (blockIdx.x < sc.n_ring_ctas && sc.n_ring) {
+                if (threadIdx.x == 0) *claim = atomicAdd(sync + 3, 1u);
+                __syncthreads();
+                const uint32_t g = *claim;
+                if (g >= sc.n_ring) break;
+                const uint32_t ul = __ldg(order + g);
+                const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
                 ring_gather16_exact(T, ring_acc, col, reinterpret_cast<const float4 *>(in), beg, end, warp, lane);
                 __syncthreads();
-            } else {
-                float *part = warp_mem;                    // warp 0's tile buffer: free during the ring phase
-                ring_gather16_fast(part, col, reinterpret_cast<const float4 *>(in), beg, end, warp, lane);
+                if (warp == 0) {
+                    put_features16(feat, g, ring_acc[lane & 15], in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+                    publish_feature(ready, g, lane);
+                }
                 __syncthreads();
+            }
+        } else if (blockIdx.x < sc.n_ring_ctas && sc.n_chunks16) {
+            // fast mode claims chunks (HubSplit).  Thread 0 keeps one claim and one chunk record
+            // ahead: the atomic for chunk i + 2 and the record of chunk i + 1 are in flight while
+            // the CTA gathers chunk i.
+            uint4 *rec_s = reinterpret_cast<uint4 *>(ring_acc + 20);
+            const uint4 none = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+            uint32_t k_next = 0;
+            uint4 rec_next = none;
+            if (threadIdx.x == 0) {
+                const uint32_t k0 = atomicAdd(sync + 3, 1u);
+                *rec_s = k0 < sc.n_chunks16 ? __ldg(hub.chunk + k0) : none;
+                k_next = atomicAdd(sync + 3, 1u);
+            }
+#pragma unroll 1
+            for (;;) {
+                __syncthreads();
+                const uint4 ck = *rec_s;                               // {g, first entry, end entry, chunk index}
+                if (ck.x == 0xFFFFFFFFu) break;
+                if (threadIdx.x == 0) {
+                    rec_next = k_next < sc.n_chunks16 ? __ldg(hub.chunk + k_next) : none;
+                    k_next = atomicAdd(sync + 3, 1u);
+                }
+                const uint32_t g = ck.x;
+                const uint2 hi = __ldg(hub.info + g);                  // {first slot, chunks}
+                float *part = warp_mem;                    // warp 0's tile buffer: free during the ring phase
+                ring_gather16_fast(part, col, reinterpret_cast<const float4 *>(in), ck.y, ck.z, warp, lane);
+                __syncthreads();
+                if (threadIdx.x == 0) *rec_s = rec_next;               // every thread has read the old record
+                bool last = true;
                 if (threadIdx.x < 16) {
                     float sum = 0.0f;
                     for (int w = 0; w < kWarpsPerCta; ++w) sum += part[w * 16 + threadIdx.x];
                     ring_acc[threadIdx.x] = sum;
+                    if (hi.y > 1) {
+                        __stcg(hub.partial + (size_t)(hi.x + ck.w) * 16 + threadIdx.x, sum);
+                        __threadfence();
+                    }
+                }
+                if (hi.y > 1) {                                        // uniform over the CTA
+                    __syncthreads();
+                    if (threadIdx.x == 0) *claim = atomicAdd(hub.done + g, 1u);
+                    __syncthreads();
+                    last = *claim == hi.y - 1;
+                    if (last && threadIdx.x < 16) {
+                        __threadfence();
+                        float sum = 0.0f;
+                        for (uint32_t c = 0; c < hi.y; ++c) sum += __ldcg(hub.partial + (size_t)(hi.x + c) * 16 + threadIdx.x);
+                        ring_acc[threadIdx.x] = sum;
+                    }
                 }
                 __syncthreads();
-            }
-            if (warp == 0) {
-                put_features16(feat, g, ring_acc[lane & 15], in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
-                publish_feature(ready, g, lane);
+                if (last && warp == 0) {
+                    const uint32_t ul = __ldg(order + g);
+                    const uint32_t deg = __ldg(row_ptr + ul + 1) - __ldg(row_ptr + ul);
+                    put_features16(feat, g, ring_acc[lane & 15], in, ul, deg, Wv, NWv, v_begin, scale, lane);
+                    publish_feature(ready, g, lane);
+                }
             }
             __syncthreads();
         }
@@ -839,7 +970,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     // stage 0: front = the giants, one warp each; everything else is a 32-vertex tile.
     // stages 1/2: front = mid tasks (8 vertices each); tiles hold the vertices of degree < 64.
     const uint32_t n_pre = STAGE == 0 ? sc.n_giant1 : sc.n_ring + sc.n_mid;   // positions that go through feature tiles
-    const uint32_t n_front = STAGE == 0 ? sc.n_giant1 : (sc.n_mid + 7) / 8;
+    const uint32_t n_front = STAGE == 0 ? (EXACT ? sc.n_giant1 : sc.n_chunks1) : (sc.n_mid + 7) / 8;
     const uint32_t n_tiles = (sc.n_local - n_pre + kTileVerts - 1) / kTileVerts;
     const uint32_t n_heavy = n_front + n_tiles;             // dealt alternately from both ends
     const uint32_t n_tasks = n_heavy + (n_pre + kTileVerts - 1) / kTileVerts;
@@ -862,13 +993,40 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
         if (k >= n_tasks) break;
         if (k < n_heavy) {
             if (g < n_front) {
-                if constexpr (STAGE == 0) {
+                if constexpr (STAGE == 0 && EXACT) {
                     const uint32_t ul = __ldg(order + g);
                     const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-                    const float acc = EXACT ? coop_gather1(T, col, in, beg, end, lane)
-                                            : coop_gather1_fast(col, in, beg, end, lane);
+                    const float acc = coop_gather1(T, col, in, beg, end, lane);
                     put_features1(feat, g, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
                     publish_feature(ready, g, lane);
+                } else if constexpr (STAGE == 0) {
+                    const uint4 ck = __ldg(hub.chunk + g);             // front task = one chunk of a giant
+                    const uint32_t pos = ck.x;
+                    const uint2 hi = __ldg(hub.info + pos);
+                    float acc = coop_gather1_fast(col, in, ck.y, ck.z, lane);
+                    bool last = true;
+                    if (hi.y > 1) {
+                        uint32_t prev = 0;
+                        if (lane == 0) {
+                            __stcg(hub.partial + hi.x + ck.w, acc);
+                            __threadfence();
+                            prev = atomicAdd(hub.done + pos, 1u);
+                        }
+                        last = __shfl_sync(0xffffffffu, prev, 0) == hi.y - 1;
+                        if (last) {
+                            __threadfence();
+                            acc = 0.0f;                                // slots in chunk order: lane-strided, then a fixed tree
+                            for (uint32_t c = lane; c < hi.y; c += 32) acc += __ldcg(hub.partial + hi.x + c);
+#pragma unroll
+                            for (int m = 1; m < 32; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+                        }
+                    }
+                    if (last) {
+                        const uint32_t ul = __ldg(order + pos);
+                        const uint32_t deg = __ldg(row_ptr + ul + 1) - __ldg(row_ptr + ul);
+                        put_features1(feat, pos, acc, in, ul, deg, Wv, NWv, v_begin, scale, lane);
+                        publish_feature(ready, pos, lane);
+                    }
                 } else {
                     const uint32_t pos0 = sc.n_ring + 8 * g;
                     gather16_mid_task(feat, ready, order, pos0, (int)min(8u, n_pre - pos0), row_ptr, col, Wv, NWv,
@@ -911,7 +1069,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
 template <int STAGE>
 constexpr size_t stage_smem_bytes() {
     constexpr StageDims D = stage_dims(STAGE);
-    return ((D.floats() + 3) / 4 * 4 + 20 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
+    return ((D.floats() + 3) / 4 * 4 + 24 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
 }
 
 // ---- schedule construction (graph upload time) -------------------------------------------
@@ -937,6 +1095,20 @@ __global__ void degree_scatter_kernel(const uint32_t *__restrict__ row_ptr, cons
         const uint32_t pos = atomicAdd(&cursor[degree_bin(end - beg)], 1u);
         order[pos] = u;
         vrec[pos] = make_uint4(u, beg, end, Wv[u]);      // everything a tile needs about the vertex, 16 B
+    }
+}
+
+// fast-mode hub chunks of order[0, n_class): see HubSplit.  counter[0] ends up as the number of chunks.
+__global__ void hub_chunks_kernel(const uint4 *__restrict__ vrec, uint32_t n_class, uint32_t chunk_len,
+                                  uint32_t *__restrict__ counter, uint2 *__restrict__ info,
+                                  uint4 *__restrict__ chunk) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_class; g += gridDim.x * blockDim.x) {
+        const uint4 r = vrec[g];
+        const uint32_t nch = max(1u, (r.z - r.y + chunk_len - 1) / chunk_len);
+        const uint32_t base = atomicAdd(counter, nch);
+        info[g] = make_uint2(base, nch);
+        for (uint32_t c = 0; c < nch; ++c)
+            chunk[base + c] = make_uint4(g, r.y + c * chunk_len, min(r.z, r.y + (c + 1) * chunk_len), c);
     }
 }
 

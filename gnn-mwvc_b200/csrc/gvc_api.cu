@@ -288,9 +288,9 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     if (nl == 0) return 0;
     const Schedule &sc = c->sched;
     const bool exact = mode == GVC_MODE_EXACT;
-    const uint32_t n_tasks = STAGE == 0 ? (exact ? sc.n_giant1 : sc.n_chunks1) + (nl - sc.n_giant1 + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
+    const uint32_t n_tasks = STAGE == 0 ? (exact ? sc.n_giant1 - sc.n_ring1 : sc.n_chunks1) + (nl - sc.n_giant1 + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
                                         : (sc.n_mid + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
-    const unsigned want = std::max<unsigned>(STAGE == 0 ? 0u : (exact ? sc.n_ring : sc.n_chunks16),
+    const unsigned want = std::max<unsigned>(STAGE == 0 ? (exact ? sc.n_ring1 : 0u) : (exact ? sc.n_ring : sc.n_chunks16),
                                              (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
     // persistent kernel: never more CTAs than can be resident at once (warps wait on each other's
     // feature vectors; a CTA that is not running could never deliver its ring tasks)
@@ -375,10 +375,11 @@ int build_schedule(gvc_ctx *c) {
     uint32_t hist[kNumDegBins], start[kNumDegBins];
     GVC_CUDA(cudaMemcpyAsync(hist, c->d_bins.p, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));
-    uint32_t pos = 0, n_ring = 0, n_pre = 0, n_giant1 = 0;
+    uint32_t pos = 0, n_ring = 0, n_pre = 0, n_giant1 = 0, n_ring1 = 0;
     for (int b = kNumDegBins - 1; b >= 0; --b) {          // descending degree
         if (b == degree_bin(kRingMinDeg) - 1) n_ring = pos;
         if (b == degree_bin(kGiant1MinDeg) - 1) n_giant1 = pos;
+        if (b == degree_bin(kRing1MinDeg) - 1) n_ring1 = pos;
         if (b == degree_bin(kMidMinDeg) - 1) n_pre = pos;
         start[b] = pos;
         pos += hist[b];
@@ -387,6 +388,7 @@ int build_schedule(gvc_ctx *c) {
     sc.n_local = nl;
     sc.n_ring = n_ring;
     sc.n_giant1 = n_giant1;
+    sc.n_ring1 = std::min(n_ring1, n_giant1);
     sc.n_mid = n_pre - n_ring;
     sc.n_tiles = (nl - n_pre + kTileVerts - 1) / kTileVerts;
     sc.n_feat_tiles = (n_pre + kTileVerts - 1) / kTileVerts;

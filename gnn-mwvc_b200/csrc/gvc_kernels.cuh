@@ -83,6 +83,10 @@ constexpr uint32_t kRingMinDeg = GVC_RING_MIN_DEG;
 #ifndef GVC_GIANT1_MIN_DEG
 #define GVC_GIANT1_MIN_DEG 2048
 #endif
+#ifndef GVC_RING1_MIN_DEG
+#define GVC_RING1_MIN_DEG 16384
+#endif
+constexpr uint32_t kRing1MinDeg = GVC_RING1_MIN_DEG;     // stage 0, exact mode: >= a whole CTA per vertex (ring_gather1_exact)
 constexpr uint32_t kGiant1MinDeg = GVC_GIANT1_MIN_DEG;   // stage 0 (w = 1): >= one warp per vertex, below one lane    // >= : ring task (whole CTA)
 constexpr uint32_t kMidMinDeg = GVC_MID_MIN_DEG;      // >= : mid task (8 vertices per warp), below: 32-vertex tiles
 constexpr int kNumDegBins = 132;
@@ -94,6 +98,7 @@ struct Schedule {
     uint32_t n_mid;        // order[n_ring, n_ring + n_mid)  mid-degree vertices, 8 per task
     uint32_t n_ring_ctas;   // CTAs [0, n_ring_ctas) share the ring tasks before joining the task queue
     uint32_t n_giant1;      // order[0, n_giant1): deg >= kGiant1MinDeg, the single-warp tasks of stage 0 (w = 1)
+    uint32_t n_ring1;       // order[0, n_ring1): deg >= kRing1MinDeg, CTA-wide in stage 0 exact mode
     uint32_t n_tiles;       // 32-vertex tiles over order[n_ring + n_mid, n_local)
     uint32_t n_feat_tiles;  // 32-vertex feature tiles over order[0, n_ring + n_mid)
     uint32_t n_chunks16;    // fast mode: chunks the ring vertices are cut into (HubSplit), width 16
@@ -547,67 +552,61 @@ __device__ __forceinline__ void coop_load_rows16(float4 (&r)[8], const BatchIds 
     }
 }
 
+// A parked batch is stored column-major, S[c * kRingColStride + row]: the lane that chains column
+// c reads four consecutive rows with one 128-bit load (the stride of 68 floats keeps the eight
+// lanes of a quarter-warp on different banks).
+constexpr int kRingColStride = 68;
+static_assert(16 * kRingColStride <= kTileFloats, "a parked batch must fit the warp's tile buffer");
+
 __device__ __forceinline__ void coop_stage_rows16(float *__restrict__ S, const float4 (&r)[8], int lane) {
-    const int sv = lane >> 2, q = lane & 3;
+    float *dst = S + (4 * (lane & 3)) * kRingColStride + (lane >> 2);      // column 4q, row sv
 #pragma unroll
-    for (int w = 0; w < 8; ++w) *reinterpret_cast<float4 *>(S + (8 * w + sv) * 16 + 4 * q) = r[w];
+    for (int w = 0; w < 8; ++w) {
+        dst[0 * kRingColStride + 8 * w] = r[w].x;
+        dst[1 * kRingColStride + 8 * w] = r[w].y;
+        dst[2 * kRingColStride + 8 * w] = r[w].z;
+        dst[3 * kRingColStride + 8 * w] = r[w].w;
+    }
 }
 
-// The reference's sequential chain over the rows parked in S: lane c (< 16, mirrored in
-// lanes 16..31) adds column c in adjacency order, one dependent FADD per neighbour.
-__device__ __forceinline__ float chain_add16(const float *__restrict__ S, int cnt, float acc, int lane) {
-    const float *s = S + (lane & 15);
-    if (cnt == 64) {
-        // groups of 8 rows, the next group's shared-memory loads overlap the current adds
-        float va[8], vb[8];
+// The reference's sequential chain over the rows parked in S: lane c (< 16, mirrored in lanes
+// 16..31) adds column c in adjacency order, one dependent FADD per neighbour.  A window of eight
+// 128-bit loads (32 rows) stays ahead of the adds: with the other warps of the SM issuing global
+// gathers a shared-memory load takes far longer than the 16 cycles its four adds cover
+// (tools/microbench/chain_lat.cu: 5.6 ns per add with two loads ahead, 2.6 ns with eight).
+// `q` holds the first 4 * kRingWindow rows on entry (loaded before the running sum arrived).
+constexpr int kRingWindow = 5;            // 128-bit loads ahead (6 and more spill next to the two row buffers)
+__device__ __forceinline__ float chain_add16_full(const float *__restrict__ S, float4 (&q)[kRingWindow], float acc, int lane) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(S + (lane & 15) * kRingColStride);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) va[t] = s[t * 16];
-#pragma unroll
-        for (int g = 0; g < 8; g += 2) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) vb[t] = s[((g + 1) * 8 + t) * 16];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, va[t]);
-            if (g + 2 < 8) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) va[t] = s[((g + 2) * 8 + t) * 16];
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, vb[t]);
-        }
-    } else {
-        for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, s[j * 16]);
+    for (int k = 0; k < 16; ++k) {
+        const float4 a = q[k % kRingWindow];
+        if (k + kRingWindow < 16) q[k % kRingWindow] = s4[k + kRingWindow];
+        acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y);
+        acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
     }
     return acc;
 }
 
-// the same chain over a full batch of 64 rows whose first 8 values are already in registers
-// (loaded before the running sum arrived)
-__device__ __forceinline__ float chain_add16_full(const float *__restrict__ S, float (&va)[8], float acc, int lane) {
-    const float *s = S + (lane & 15);
-    float vb[8];
-#pragma unroll
-    for (int g = 0; g < 8; g += 2) {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) vb[t] = s[((g + 1) * 8 + t) * 16];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, va[t]);
-        if (g + 2 < 8) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) va[t] = s[((g + 2) * 8 + t) * 16];
-        }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, vb[t]);
-    }
+// partial batch (the end of the list)
+__device__ __forceinline__ float chain_add16(const float *__restrict__ S, int cnt, float acc, int lane) {
+    const float *s = S + (lane & 15) * kRingColStride;
+    for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, s[j]);
     return acc;
 }
 
 // ring task, width 16: the 8 warps of the CTA serve one vertex.  Warp w fetches batches
 // w, w+8, ... (64 rows each) into its own tile buffer; the running sum travels from warp
 // to warp through shared memory, the hand-over for batch b is named barrier 1 + b % 8
-// (arrive by the warp that summed b-1, sync by the warp that sums b; polling a {value, sequence
-// number} slot instead of the barrier was measured slower: 4.5 vs 3.9 ns per neighbour).  All 8
-// warps call this; the caller reads the 16 sums from ring_acc after a __syncthreads().
+// (arrive by the warp that summed b-1, sync by the warp that sums b).  All 8 warps call this;
+// the caller reads the 16 sums from ring_acc after a __syncthreads().
+// Measured on a 262144-neighbour star (tools/chain_probe.py): 3.9 ns per neighbour against 2.07 ns
+// for a bare chain of dependent FADDs (tools/microbench/chain_lat.cu: 4 cycles).  Tried and not
+// faster: polling a {value, sequence number} slot instead of the barrier (4.5 ns); one warp that
+// only chains, fed by 7 loader warps through full/empty barriers (4.4 ns; 4.0 ns with the parked
+// batch stored column-major for 128-bit loads; 4.0 ns with both register buffers of every loader
+// in flight).  The same microbenchmark shows why: a chain warp whose neighbours on the SM issue
+// global gathers drops to 5.5 ns per add -- the loaders themselves are the interference.
 __device__ __noinline__ void ring_gather16_exact(float *__restrict__ S, float *__restrict__ ring_acc,
                                               const uint32_t *__restrict__ col,
                                               const float4 *__restrict__ in4, uint32_t beg, uint32_t end,
@@ -633,10 +632,11 @@ __device__ __noinline__ void ring_gather16_exact(float *__restrict__ S, float *_
         coop_stage_rows16(S, r, lane);
         __syncwarp();
         const int cnt = (int)min(64u, end - e0);
-        float va[8];
-        if (cnt == 64) {                       // first values of the batch: on hand before the sum arrives
+        float4 va[kRingWindow];
+        if (cnt == 64) {                       // first rows of the batch: on hand before the sum arrives
+            const float4 *s4 = reinterpret_cast<const float4 *>(S + (lane & 15) * kRingColStride);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) va[t] = S[t * 16 + (lane & 15)];
+            for (int t = 0; t < kRingWindow; ++t) va[t] = s4[t];
         }
         float acc = 0.0f;
         if (b > 0) {
@@ -695,7 +695,8 @@ __device__ __noinline__ void ring_gather16_fast(float *__restrict__ part, const 
 // summed.  The block is parked in shared memory and every lane walks it with broadcast 128-bit
 // loads.  Measured alternatives, both slower (3.4 ns per neighbour here): cp.async of the single
 // values straight into a shared-memory ring (4.4 ns), and the prefetch code placed behind the
-// fully unrolled chain's first loads so that the scheduler can interleave them (3.95 ns).
+// fully unrolled chain's first loads so that the scheduler can interleave them (3.95 ns); a window
+// of eight shared-memory loads ahead of the adds as in the width-16 chain (3.5 ns).
 constexpr int kGiant1Depth = 4;
 
 __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 floats */,
@@ -778,6 +779,93 @@ __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 float
         __syncwarp();
     }
     return acc;
+}
+
+// CTA-wide task, width 1, exact mode (the few vertices of degree >= kRing1MinDeg in stage 0).
+// As a single-warp task (coop_gather1) the chain warp also fetches, and shares its scheduler with
+// warps running dense tiles: ~35 % of its time goes into the fetch code, and on a busy SM it falls
+// from 3.1 to ~5 ns per neighbour -- the longest of these chains is the critical path of stage 0.
+// Here warp 0 does nothing but the chain (the sum stays in its registers), warps 1..7 fetch:
+// loader i gathers blocks i, i+7, ... (256 neighbours each) into its own tile buffer, one block
+// parked, one in registers, ids one further ahead.  full[i]/empty[i] named barriers as a
+// producer/consumer pair per buffer; the chain warp syncs on the next buffer before it sums the
+// current one.  Returns the sum in warp 0 (other warps: 0).
+constexpr int kRing1Loaders = kWarpsPerCta - 1;
+static_assert(kRing1Loaders >= 2 && 2 * kRing1Loaders + 1 <= 16, "two named barriers per loader, ids 1..15");
+
+__device__ __noinline__ float ring_gather1_exact(float *__restrict__ warp_mem, const uint32_t *__restrict__ col,
+                                                 const float *__restrict__ x, uint32_t beg, uint32_t end,
+                                                 int warp, int lane) {
+    constexpr int L = kRing1Loaders;
+    constexpr int kFull = 1, kEmpty = 1 + L;
+    const uint32_t nb = (end - beg + 255) / 256;
+    if (nb == 0) return 0.0f;
+    if (warp == 0) {
+        float acc = 0.0f;
+        named_bar_sync(kFull, 64);
+#pragma unroll 1
+        for (uint32_t b = 0; b < nb; ++b) {
+            const int i = (int)(b % L);
+            const float *S = warp_mem + (1 + i) * kWarpSmemFloats;
+            if (b + 1 < nb) named_bar_sync(kFull + (int)((b + 1) % L), 64);     // normally full long since
+            const int cnt = (int)min(256u, end - (beg + 256 * b));
+            const float4 *s4 = reinterpret_cast<const float4 *>(S);
+            int j = 0;
+            if (cnt == 256) {
+                // the next 16 values are loaded while the current 16 are added (a rolled loop with a
+                // window of 32 values ahead was measured slower: 3.25 vs 2.85 ns per neighbour)
+                float4 a = s4[0], bq = s4[1], c = s4[2], d = s4[3];
+#pragma unroll 4
+                for (; j < 256; j += 16) {
+                    const int n4 = (j + 16 < 256) ? (j + 16) / 4 : 0;
+                    const float4 na = s4[n4], nb4 = s4[n4 + 1], nc = s4[n4 + 2], nd = s4[n4 + 3];
+                    acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
+                    acc = __fadd_rn(acc, bq.x); acc = __fadd_rn(acc, bq.y); acc = __fadd_rn(acc, bq.z); acc = __fadd_rn(acc, bq.w);
+                    acc = __fadd_rn(acc, c.x); acc = __fadd_rn(acc, c.y); acc = __fadd_rn(acc, c.z); acc = __fadd_rn(acc, c.w);
+                    acc = __fadd_rn(acc, d.x); acc = __fadd_rn(acc, d.y); acc = __fadd_rn(acc, d.z); acc = __fadd_rn(acc, d.w);
+                    a = na; bq = nb4; c = nc; d = nd;
+                }
+            }
+            for (; j < cnt; ++j) acc = __fadd_rn(acc, S[j]);
+            __syncwarp();
+            if (b + L < nb) named_bar_arrive(kEmpty + i, 64);  // loader i has another block for this buffer
+        }
+        return acc;
+    }
+    // ---- loader i = warp - 1 -----------------------------------------------------------------
+    const int i = warp - 1;
+    float *S = warp_mem + warp * kWarpSmemFloats;
+    uint32_t id[8];
+    float v[8], vn[8];
+    auto ld_ids = [&](uint32_t blk) {
+        const uint32_t e0 = beg + 256 * blk, lim = blk < nb ? end : 0u;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < lim) ? ld_id(col + e) : 0u; }
+    };
+    auto ld_x = [&](float (&val)[8], uint32_t blk) {
+        const uint32_t e0 = beg + 256 * blk, lim = blk < nb ? end : 0u;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; val[t] = (e < lim) ? __ldg(x + id[t]) : 0.0f; }
+    };
+    uint32_t b = i;
+    ld_ids(b);
+    ld_x(v, b);
+    ld_ids(b + L);
+    bool first = true;
+#pragma unroll 1
+    for (; b < nb; b += L) {
+        ld_x(vn, b + L);                                       // next block's values in flight
+        ld_ids(b + 2 * L);
+        if (!first) named_bar_sync(kEmpty + i, 64);            // the chain has read the previous contents
+        first = false;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) S[32 * t + lane] = v[t];
+        __threadfence_block();
+        named_bar_arrive(kFull + i, 64);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = vn[t];
+    }
+    return 0.0f;
 }
 
 // fast mode: every lane sums its own elements, one shuffle reduction at the end; the values of
@@ -884,6 +972,26 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     // ---- ring tasks (width 16 only): the whole CTA, largest vertices first --------------------
     // With w = 1 the chain costs the same 4 cycles per neighbour whoever feeds it and one warp
     // can keep its own loads ahead, so stage 0 runs the giants as single-warp tasks instead.
+    if constexpr (STAGE == 0 && EXACT) {
+        // stage 0, exact mode: the few vertices whose sequential sum is long enough to be the
+        // critical path of the stage get a whole CTA (ring_gather1_exact), largest first
+        uint32_t *claim = reinterpret_cast<uint32_t *>(ring_acc) + 16;
+#pragma unroll 1
+        while (blockIdx.x < sc.n_ring_ctas && sc.n_ring1) {
+            if (threadIdx.x == 0) *claim = atomicAdd(sync + 3, 1u);
+            __syncthreads();
+            const uint32_t g = *claim;
+            if (g >= sc.n_ring1) break;
+            const uint32_t ul = __ldg(order + g);
+            const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
+            const float acc = ring_gather1_exact(warp_mem, col, in, beg, end, warp, lane);
+            if (warp == 0) {
+                put_features1(feat, g, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+                publish_feature(ready, g, lane);
+            }
+            __syncthreads();
+        }
+    }
     if constexpr (STAGE != 0) {
         // claimed one at a time, largest first: a CTA that drew a huge vertex takes fewer of them
         uint32_t *claim = reinterpret_cast<uint32_t *>(ring_acc) + 16;
@@ -970,7 +1078,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     // stage 0: front = the giants, one warp each; everything else is a 32-vertex tile.
     // stages 1/2: front = mid tasks (8 vertices each); tiles hold the vertices of degree < 64.
     const uint32_t n_pre = STAGE == 0 ? sc.n_giant1 : sc.n_ring + sc.n_mid;   // positions that go through feature tiles
-    const uint32_t n_front = STAGE == 0 ? (EXACT ? sc.n_giant1 : sc.n_chunks1) : (sc.n_mid + 7) / 8;
+    const uint32_t n_front = STAGE == 0 ? (EXACT ? sc.n_giant1 - sc.n_ring1 : sc.n_chunks1) : (sc.n_mid + 7) / 8;
     const uint32_t n_tiles = (sc.n_local - n_pre + kTileVerts - 1) / kTileVerts;
     const uint32_t n_heavy = n_front + n_tiles;             // dealt alternately from both ends
     const uint32_t n_tasks = n_heavy + (n_pre + kTileVerts - 1) / kTileVerts;
@@ -994,11 +1102,12 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
         if (k < n_heavy) {
             if (g < n_front) {
                 if constexpr (STAGE == 0 && EXACT) {
-                    const uint32_t ul = __ldg(order + g);
+                    const uint32_t pos = sc.n_ring1 + g;               // the largest went through the ring phase
+                    const uint32_t ul = __ldg(order + pos);
                     const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
                     const float acc = coop_gather1(T, col, in, beg, end, lane);
-                    put_features1(feat, g, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
-                    publish_feature(ready, g, lane);
+                    put_features1(feat, pos, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
+                    publish_feature(ready, pos, lane);
                 } else if constexpr (STAGE == 0) {
                     const uint4 ck = __ldg(hub.chunk + g);             // front task = one chunk of a giant
                     const uint32_t pos = ck.x;

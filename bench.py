@@ -266,8 +266,11 @@ def run_ours(args):
     if world > 1:
         ctx.graph_set_tail(int(_perm[n - 1].item()) if n % 2 else None)
     stream = ctx.torch_stream()
-    h1 = torch.zeros(g.n, 16, device=dev)
-    h2 = torch.zeros(g.n, 16, device=dev)
+    # N > 1: the stage kernels store their rows straight into the other ranks' h1/h2 over NVLink
+    # (peer memory); --exchange nccl all-gathers them between the stages instead
+    pr = gdist.PeerRows(ctx, g.n) if world > 1 and args.exchange == "peer" else None
+    h1 = pr.h1 if pr else torch.zeros(g.n, 16, device=dev)
+    h2 = pr.h2 if pr else torch.zeros(g.n, 16, device=dev)
     scores = torch.zeros(shard.n_local, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     torch.cuda.synchronize()
@@ -276,7 +279,7 @@ def run_ours(args):
         if world == 1:
             ctx.forward_device(x_full, weight_scale, scores, mode)
         else:
-            gdist.sharded_forward(ctx.stage_device, shard, x_full, h1, h2, scores, weight_scale, mode)
+            gdist.sharded_forward(ctx.stage_device, shard, x_full, h1, h2, scores, weight_scale, mode, peer_rows=pr)
 
     def barrier():
         if world > 1:
@@ -313,9 +316,9 @@ def run_ours(args):
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
                 ev[0].record(stream)
                 ctx.stage_device(0, x_full, h1, weight_scale, mode); ev[1].record(stream)
-                gdist.exchange_rows(h1, bounds, None, shard.live); ev[2].record(stream)
+                (pr.barrier() if pr else gdist.exchange_rows(h1, bounds, None, shard.live)); ev[2].record(stream)
                 ctx.stage_device(1, h1, h2, weight_scale, mode); ev[3].record(stream)
-                gdist.exchange_rows(h2, bounds, None, shard.live); ev[4].record(stream)
+                (pr.barrier() if pr else gdist.exchange_rows(h2, bounds, None, shard.live)); ev[4].record(stream)
                 ctx.stage_device(2, h2, scores, weight_scale, mode); ev[5].record(stream)
                 ev[5].synchronize()
                 for i, k in enumerate(names):
@@ -425,7 +428,7 @@ def run_ours(args):
                     ctx.graph_upload(srp, scol, sW, sNW, n_global=g.n, v_begin=shard.v_begin, v_end=shard.v_end)
                     ctx.graph_set_tail(tail)
                 xd.copy_(xp, non_blocking=True)
-                gdist.sharded_forward(ctx.stage_device, shard, xd, h1, h2, scores, weight_scale, mode)
+                gdist.sharded_forward(ctx.stage_device, shard, xd, h1, h2, scores, weight_scale, mode, peer_rows=pr)
                 sp.copy_(scores, non_blocking=True)
                 stream.synchronize()
             times = {}
@@ -480,7 +483,7 @@ def run_ours(args):
             "config": {"workload": wl_name, "vertices": n, "edges": e_total, "nnz": m, "mode": args.mode,
                        "weights": "trained GNN_VC model (tests/golden/mwvc_model.npz)",
                        "l2": "256 MiB flush write between timed steps; working set (CSR + rows) also exceeds the 126 MB L2",
-                       "sharding": "single GPU" if world == 1 else f"{world} equal vertex ranges of the relabelled graph (vertices dealt to the shards by descending degree: equal counts, equal nnz), NCCL all-gather of the 16-float rows of the non-isolated vertices after stages 0 and 1",
+                       "sharding": "single GPU" if world == 1 else f"{world} equal vertex ranges of the relabelled graph (vertices dealt to the shards by descending degree: equal counts, equal nnz), " + ("the stage kernels store the 16-float rows of the non-isolated vertices into every other rank's h buffers over NVLink (CUDA IPC peer memory), a one-element NCCL all-reduce as barrier after stages 0 and 1" if pr else "NCCL all-gather of the 16-float rows of the non-isolated vertices after stages 0 and 1"),
                        "graph_generation_s": round(gen_s, 2)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "phase_ms": phase_ms, "other_mode": other,
@@ -503,6 +506,8 @@ def main():
     ap.add_argument("--workload", default="rmat", choices=["rmat", "grid", "er", "isolated"])
     ap.add_argument("--scale", type=int, default=0, help="override the R-MAT scale")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: rows delivered by the stage kernels through peer memory, or NCCL all-gathers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

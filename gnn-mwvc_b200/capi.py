@@ -36,6 +36,11 @@ SIGNATURES = {
                                     C.POINTER(_u32p), C.POINTER(_u32p)]),
     "gvc_graph_adopt_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gvc_graph_set_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
+    "gvc_peer_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "gvc_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "gvc_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gvc_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gvc_stage_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gvc_forward": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, C.c_int]),
     "gvc_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]),
     "gvc_stage_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int]),
@@ -196,6 +201,31 @@ class Context:
             self._check(self.lib.gvc_graph_set_tail(self.h, 1, global_vertex - self.v_begin))
         else:
             self._check(self.lib.gvc_graph_set_tail(self.h, 0, 0))
+
+    # -- peer memory (multi-GPU row exchange inside the stage kernels) -------------
+    def peer_alloc(self, nbytes: int):
+        """(device pointer, 64-byte IPC handle) of a fresh zeroed buffer other processes can map."""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self._check(self.lib.gvc_peer_alloc(self.h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self.lib.gvc_peer_open(self.h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int):
+        self._check(self.lib.gvc_peer_close(self.h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int):
+        self._check(self.lib.gvc_peer_free(self.h, C.c_void_p(ptr)))
+
+    def stage_peers(self, stage: int, ptrs):
+        """Mirror the output rows of `stage` (0 or 1) into these mapped buffers of the other ranks."""
+        arr = (C.c_void_p * max(len(ptrs), 1))(*ptrs)
+        self._check(self.lib.gvc_stage_peers(self.h, stage, len(ptrs), arr))
 
     # -- forward ---------------------------------------------------------------
     def forward(self, x, weight_scale: float, mode: int = MODE_EXACT) -> np.ndarray:

@@ -136,6 +136,8 @@ struct gvc_ctx {
     DevBuf<float> d_hub_partial[2];
     DevBuf<uint32_t> d_hub_count;
     gvc::Schedule sched{};
+    gvc::PeerOut peers[2] = {};          // stage 0 / stage 1 outputs mirrored into the other ranks' buffers
+    uint32_t n_live = 0;                 // positions of `order` with a non-empty adjacency list
     int num_sms = 148;
     int ctas_per_sm[3] = {1, 1, 1};      // resident CTAs per SM of each stage kernel (occupancy query)
 
@@ -299,6 +301,9 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     sc_launch.n_ring_ctas = std::min<unsigned>(grid, (unsigned)c->num_sms);   // one ring CTA per SM at most
     const size_t smem = stage_smem_bytes<STAGE>();
     // task counter + per-feature-tile completion counters start at zero
+    PeerOut peers{};
+    if (STAGE < 2) peers = c->peers[STAGE];
+    peers.n_live = c->n_live;
     const int hk = STAGE == 0 ? 1 : 0;
     const uint32_t n_split = STAGE == 0 ? sc.n_giant1 : sc.n_ring;
     HubSplit hub{c->d_hub_chunk[hk].p, c->d_hub_info[hk].p, c->d_hub_partial[hk].p,
@@ -306,11 +311,11 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (kSyncCounters + (size_t)sc.n_feat_tiles + (exact ? 0 : n_split)) * sizeof(uint32_t), c->stream));
     if (mode == GVC_MODE_EXACT) {
         stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, hub, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, hub, peers, c->d_feat.p, c->d_sync.p, d_in, d_out,
             c->d_stage_params[STAGE], c->v_begin, scale);
     } else {
         stage_kernel<STAGE, false><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, hub, c->d_feat.p, c->d_sync.p, d_in, d_out,
+            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, hub, peers, c->d_feat.p, c->d_sync.p, d_in, d_out,
             c->d_stage_params[STAGE], c->v_begin, scale);
     }
     GVC_CUDA(cudaGetLastError());
@@ -321,7 +326,7 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     if (mode == GVC_MODE_EXACT && has_tail) {
         const uint32_t tail = c->tail_override == 1 ? c->tail_local : nl - 1;
         stage_tail_kernel<STAGE><<<1, 32, 0, c->stream>>>(c->row_ptr, c->col, c->Wv, c->NWv, d_in, d_out,
-                                                          c->d_stage_params[STAGE], tail, c->v_begin, scale);
+                                                          c->d_stage_params[STAGE], tail, c->v_begin, scale, peers);
         GVC_CUDA(cudaGetLastError());
         c->launches++;
     }
@@ -384,6 +389,7 @@ int build_schedule(gvc_ctx *c) {
         start[b] = pos;
         pos += hist[b];
     }
+    c->n_live = nl - hist[0];                            // bin 0 = degree 0, the end of `order`
     Schedule &sc = c->sched;
     sc.n_local = nl;
     sc.n_ring = n_ring;
@@ -525,7 +531,7 @@ int set_graph_views(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_
 extern "C" {
 
 const char *gvc_last_error(void) { return g_err.c_str(); }
-int gvc_abi_version(void) { return 2; }
+int gvc_abi_version(void) { return 3; }
 
 int gvc_ctx_create(gvc_ctx **out, int device) {
     if (!out) return fail(GVC_ERR_ARG, "out is null");
@@ -748,6 +754,76 @@ int gvc_graph_set_tail(gvc_ctx *c, int has_tail, uint32_t local_index) {
     if (has_tail && local_index >= c->n_local()) return fail(GVC_ERR_ARG, "tail vertex %u outside the shard", local_index);
     c->tail_override = has_tail ? 1 : 0;
     c->tail_local = local_index;
+    return 0;
+}
+
+int gvc_peer_alloc(gvc_ctx *c, uint64_t bytes, void **d_ptr, unsigned char *handle) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!d_ptr || !handle || !bytes) return fail(GVC_ERR_ARG, "null argument");
+    if ((rc = use_device(c))) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == GVC_PEER_HANDLE_BYTES, "handle size");
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(GVC_ERR_ALLOC, "cudaMalloc(%llu bytes): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(1000 + (int)e, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    GVC_CUDA(cudaMemsetAsync(p, 0, bytes, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    std::memcpy(handle, &h, sizeof(h));
+    *d_ptr = p;
+    return 0;
+}
+
+int gvc_peer_open(gvc_ctx *c, const unsigned char *handle, void **d_ptr) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!d_ptr || !handle) return fail(GVC_ERR_ARG, "null argument");
+    if ((rc = use_device(c))) return rc;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(1000 + (int)e, "cudaIpcOpenMemHandle: %s (peer access between the two GPUs is required)", cudaGetErrorString(e));
+    *d_ptr = p;
+    return 0;
+}
+
+int gvc_peer_close(gvc_ctx *c, void *d_ptr) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if ((rc = use_device(c))) return rc;
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto &po : c->peers)
+        for (int q = 0; q < po.n; ++q)
+            if (po.p[q] == d_ptr) po.n = 0;                  // never keep a pointer that is about to vanish
+    GVC_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+int gvc_peer_free(gvc_ctx *c, void *d_ptr) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if ((rc = use_device(c))) return rc;
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    GVC_CUDA(cudaFree(d_ptr));
+    return 0;
+}
+
+int gvc_stage_peers(gvc_ctx *c, int stage, int n_peers, float *const *d_out_peers) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (stage != 0 && stage != 1) return fail(GVC_ERR_ARG, "only stages 0 and 1 write rows that other shards read");
+    if (n_peers < 0 || n_peers > kMaxPeers) return fail(GVC_ERR_UNSUPPORTED, "%d peers; at most %d (8 GPUs)", n_peers, kMaxPeers);
+    if (n_peers && !d_out_peers) return fail(GVC_ERR_ARG, "null peer table");
+    PeerOut po{};
+    for (int q = 0; q < n_peers; ++q) {
+        if (!d_out_peers[q]) return fail(GVC_ERR_ARG, "peer %d is null", q);
+        po.p[q] = d_out_peers[q];
+    }
+    po.n = n_peers;
+    c->peers[stage] = po;
     return 0;
 }
 

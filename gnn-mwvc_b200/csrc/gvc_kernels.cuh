@@ -119,6 +119,17 @@ struct Schedule {
 #endif
 constexpr uint32_t kChunk16 = GVC_CHUNK16;
 constexpr uint32_t kChunk1 = GVC_CHUNK1;
+// Multi-GPU: the other ranks' copies of this stage's output buffer (peer memory over NVLink).  The
+// store epilogue writes every row that another rank can read -- the rows of non-isolated vertices,
+// positions [0, n_live) of `order` -- into all of them, so the row exchange between two stages is
+// part of the kernel and overlaps its compute; what remains between stages is a barrier.
+constexpr int kMaxPeers = 7;
+struct PeerOut {
+    float *p[kMaxPeers];
+    int n;                  // 0: single GPU, or rows exchanged by a collective instead
+    uint32_t n_live;        // positions of `order` below this hold vertices with neighbours
+};
+
 struct HubSplit {
     const uint4 *chunk;
     const uint2 *info;
@@ -228,7 +239,8 @@ __device__ __forceinline__ void tile_linear_relu_store16(const float *__restrict
                                                          const float *__restrict__ bsm, int lane,
                                                          float *__restrict__ out /* global row 0 */,
                                                          const uint32_t *__restrict__ vid /* smem: global vertex id per slot */,
-                                                         int valid /* slots of the tile that hold a vertex */) {
+                                                         int valid /* slots of the tile that hold a vertex */,
+                                                         const PeerOut &peers, int live /* leading slots other ranks read */) {
     const int og = lane >> 3, vg = lane & 7;
     float acc[4][4];
 #pragma unroll
@@ -256,7 +268,12 @@ __device__ __forceinline__ void tile_linear_relu_store16(const float *__restrict
             o.y = relu_ref(__fadd_rn(acc[r][1], b.y));
             o.z = relu_ref(__fadd_rn(acc[r][2], b.z));
             o.w = relu_ref(__fadd_rn(acc[r][3], b.w));
-            *reinterpret_cast<float4 *>(out + (size_t)vid[i] * 16 + 4 * og) = o;
+            const size_t at = (size_t)vid[i] * 16 + 4 * og;
+            *reinterpret_cast<float4 *>(out + at) = o;
+            if (i < live) {
+#pragma unroll 1
+                for (int q = 0; q < peers.n; ++q) *reinterpret_cast<float4 *>(peers.p[q] + at) = o;
+            }
         }
     }
 }
@@ -272,7 +289,8 @@ __device__ __forceinline__ float sigmoid_ref(float v) {
 template <int STAGE, bool EXACT>
 __device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const uint32_t *__restrict__ vid,
                                                      int count, const float *__restrict__ P,
-                                                     float *__restrict__ out, uint32_t v_begin, int lane) {
+                                                     float *__restrict__ out, uint32_t v_begin, int lane,
+                                                     const PeerOut &peers, int live) {
     constexpr StageDims D = stage_dims(STAGE);
     const float *Wa = P, *ba = Wa + D.Ka * D.Na;
     const float *Wb = ba + D.Na, *bb = Wb + D.Kb * D.Nb;
@@ -284,7 +302,7 @@ __device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const u
     tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane);
     tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane);
     if constexpr (STAGE < 2) {
-        tile_linear_relu_store16<D.Kc, EXACT>(T, Wc, bc, lane, out, vid, count);
+        tile_linear_relu_store16<D.Kc, EXACT>(T, Wc, bc, lane, out, vid, count, peers, live);
     } else {
         // 16 -> 1: one lane per vertex.  OpenBLAS' 1-column kernel: even/odd
         // accumulators, C = even + odd (oracle/gnn_oracle.c dot_two_acc).
@@ -951,17 +969,20 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
              const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
              const uint32_t *__restrict__ order, const uint4 *__restrict__ vrec, const Schedule sc,
-             const HubSplit hub, float *__restrict__ feat,
+             const HubSplit hub, const PeerOut peers_arg, float *__restrict__ feat,
              uint32_t *__restrict__ sync, const float *__restrict__ in, float *__restrict__ out,
              const float *__restrict__ params, uint32_t v_begin, float scale) {
     constexpr StageDims D = stage_dims(STAGE);
     extern __shared__ __align__(16) float smem[];
     float *P = smem;                                             // packed parameters
     constexpr int kParamFloats = (D.floats() + 3) / 4 * 4;
-    float *ring_acc = smem + kParamFloats;                       // 16 sums, the CTA's ring claim [16], a chunk record [20..23]
-    float *warp_mem = ring_acc + 24;
+    float *ring_acc = smem + kParamFloats;                       // 16 sums, the CTA's ring claim [16], a chunk record [20..23],
+    PeerOut &peers = *reinterpret_cast<PeerOut *>(ring_acc + 24);   // the peer table [24..39] (shared memory: passed by reference)
+    static_assert(sizeof(PeerOut) == 64, "PeerOut is laid out in 16 floats of shared memory");
+    float *warp_mem = ring_acc + 40;
 
     for (int i = threadIdx.x; i < D.floats(); i += kCtaThreads) P[i] = __ldg(params + i);
+    if (threadIdx.x == 0) peers = peers_arg;
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1150,7 +1171,8 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
                 else
                     gather16_tile(T, vid, vrec, pos0, count, col, NWv,
                                   reinterpret_cast<const float4 *>(in), v_begin, scale, lane);
-                tile_dense_and_store<STAGE, EXACT>(T, vid, count, P, out, v_begin, lane);
+                const int live = peers.n_live > pos0 ? (int)min((uint32_t)count, peers.n_live - pos0) : 0;
+                tile_dense_and_store<STAGE, EXACT>(T, vid, count, P, out, v_begin, lane, peers, live);
             }
         } else {
             // feature tile: 32 precomputed feature vectors -> dense + store
@@ -1170,7 +1192,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
                     T[lane * kTileStride + i] = (i < count) ? __ldcg(feat + (size_t)(pos0 + i) * 32 + lane) : 0.0f;
             }
             __syncwarp();
-            tile_dense_and_store<STAGE, EXACT>(T, vid, count, P, out, v_begin, lane);
+            tile_dense_and_store<STAGE, EXACT>(T, vid, count, P, out, v_begin, lane, peers, count);   // degree >= 64: all live
         }
     }
 }
@@ -1178,7 +1200,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
 template <int STAGE>
 constexpr size_t stage_smem_bytes() {
     constexpr StageDims D = stage_dims(STAGE);
-    return ((D.floats() + 3) / 4 * 4 + 24 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
+    return ((D.floats() + 3) / 4 * 4 + 40 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
 }
 
 // ---- schedule construction (graph upload time) -------------------------------------------
@@ -1230,7 +1252,7 @@ __global__ void __launch_bounds__(32)
 stage_tail_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
                   const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
                   const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ params,
-                  uint32_t ul, uint32_t v_begin, float scale) {
+                  uint32_t ul, uint32_t v_begin, float scale, const PeerOut peers) {
     constexpr StageDims D = stage_dims(STAGE);
     __shared__ float f[2][32];
     const int lane = threadIdx.x;
@@ -1279,8 +1301,12 @@ stage_tail_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restri
     if (lane < D.Nb) f[0][lane] = relu_ref(__fadd_rn(dot2(f[1], Wb, D.Kb, D.Nb, lane), bb[lane]));
     __syncwarp();
     if constexpr (STAGE < 2) {
-        if (lane < 16)
-            out[(size_t)(v_begin + ul) * 16 + lane] = relu_ref(__fadd_rn(dot2(f[0], Wc, D.Kc, 16, lane), bc[lane]));
+        if (lane < 16) {
+            const float o = relu_ref(__fadd_rn(dot2(f[0], Wc, D.Kc, 16, lane), bc[lane]));
+            out[(size_t)(v_begin + ul) * 16 + lane] = o;
+            if (end > beg)
+                for (int q = 0; q < peers.n; ++q) peers.p[q][(size_t)(v_begin + ul) * 16 + lane] = o;
+        }
     } else {
         if (lane == 0) {   // 1 row x 1 column kernel: four accumulators, (c0+c1)+(c2+c3)
             float c[4] = {0.f, 0.f, 0.f, 0.f};

@@ -80,22 +80,90 @@ def exchange_rows(full: torch.Tensor, bounds, group=None, live=None) -> None:
                 dist.broadcast(views[r], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
 
 
+class PeerRows:
+    """``h1``/``h2`` in buffers every rank of the node has mapped (CUDA IPC over NVLink): the stage
+    kernels of this rank's context store each row another shard may read straight into the other
+    ranks' copies (``gvc_stage_peers``), so the exchange between two stages shrinks to a barrier.
+    One process per GPU, at most 8 ranks, NCCL group for the handle exchange and the barrier."""
+
+    def __init__(self, ctx, n_global: int, group=None):
+        self.ctx, self.group = ctx, group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", ctx.device)
+        nbytes = int(n_global) * 16 * 4
+        self.own, handles = [], b""
+        for _ in range(2):
+            ptr, h = ctx.peer_alloc(nbytes)
+            self.own.append(ptr)
+            handles += h
+        mine = torch.tensor(list(handles), dtype=torch.uint8, device=dev)
+        everybody = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(everybody, mine, group=group)
+        self.mapped = [[], []]
+        for r in range(world):
+            if r == rank:
+                continue
+            hb = bytes(everybody[r].cpu().tolist())
+            for k in range(2):
+                self.mapped[k].append(ctx.peer_open(hb[64 * k:64 * (k + 1)]))
+        ctx.stage_peers(0, self.mapped[0])
+        ctx.stage_peers(1, self.mapped[1])
+        self.h1 = _as_tensor(self.own[0], (int(n_global), 16), dev)
+        self.h2 = _as_tensor(self.own[1], (int(n_global), 16), dev)
+        self._token = torch.zeros(1, device=dev)
+
+    def barrier(self) -> None:
+        """Every rank's stage kernel (and with it its stores into our buffers) has finished: a
+        one-element all-reduce ordered on the current stream, no host synchronisation."""
+        dist.all_reduce(self._token, group=self.group)
+
+    def close(self) -> None:
+        self.ctx.stage_peers(0, [])
+        self.ctx.stage_peers(1, [])
+        torch.cuda.synchronize()
+        dist.barrier(self.group)                 # nobody still writes into a buffer that is about to go
+        for k in range(2):
+            for p in self.mapped[k]:
+                self.ctx.peer_close(p)
+        dist.barrier(self.group)
+        self.h1 = self.h2 = None
+        for p in self.own:
+            self.ctx.peer_free(p)
+
+
+class _RawCuda:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2,
+                                         "strides": None}
+
+
+def _as_tensor(ptr: int, shape, dev) -> torch.Tensor:
+    return torch.as_tensor(_RawCuda(ptr, shape), device=dev)
+
+
 def sharded_forward(stage_fn, shard: Shard, x_full: torch.Tensor, h1: torch.Tensor, h2: torch.Tensor,
                     scores_local: torch.Tensor, weight_scale: float, mode: int, group=None,
-                    before_exchange=None) -> None:
+                    before_exchange=None, peer_rows: PeerRows = None) -> None:
     """The three stages with the two row exchanges between them.
 
     stage_fn(stage, d_in, d_out, weight_scale, mode) enqueues one fused stage for this rank's
     shard (``Context.stage_device``).  ``before_exchange()`` must make the stage's output
-    visible to the communication stream (stream sync for CUDA; nothing on CPU)."""
+    visible to the communication stream (stream sync for CUDA; nothing on CPU).  With
+    ``peer_rows`` (h1/h2 must be its buffers) the kernels have already delivered the rows and
+    the exchange is a barrier."""
+    def exchange(h):
+        if peer_rows is not None:
+            peer_rows.barrier()
+        else:
+            exchange_rows(h, shard.bounds, group, shard.live)
     stage_fn(0, x_full, h1, weight_scale, mode)
     if before_exchange:
         before_exchange()
-    exchange_rows(h1, shard.bounds, group, shard.live)
+    exchange(h1)
     stage_fn(1, h1, h2, weight_scale, mode)
     if before_exchange:
         before_exchange()
-    exchange_rows(h2, shard.bounds, group, shard.live)
+    exchange(h2)
     stage_fn(2, h2, scores_local, weight_scale, mode)
 
 

@@ -151,6 +151,24 @@ int gvc_forward_device(gvc_ctx *ctx, const float *d_x, float weight_scale, float
 int gvc_stage_device(gvc_ctx *ctx, int stage, const float *d_in, float *d_out,
                      float weight_scale, int mode);
 
+/* ---- multi-GPU: row exchange through peer memory --------------------------
+ * One process per GPU.  Instead of all-gathering the 16-float rows between two
+ * stages (gnn-mwvc_b200/dist.py exchange_rows), the store epilogue of stages 0
+ * and 1 can write every row that another shard may read straight into the other
+ * ranks' copies of the output buffer over NVLink; between stages the ranks then
+ * only need a barrier.  The buffers must be reachable from this device:
+ * gvc_peer_alloc allocates one and returns its CUDA IPC handle (64 bytes, to be
+ * sent to the other processes by any means), gvc_peer_open maps a buffer another
+ * process allocated, gvc_stage_peers(stage, n, ptrs) registers the n <= 7 mapped
+ * buffers that mirror d_out of that stage (n = 0 switches the mirroring off).
+ * Rows of isolated vertices are not mirrored (nobody reads them). */
+#define GVC_PEER_HANDLE_BYTES 64
+int gvc_peer_alloc(gvc_ctx *ctx, uint64_t bytes, void **d_ptr, unsigned char *handle);
+int gvc_peer_open(gvc_ctx *ctx, const unsigned char *handle, void **d_ptr);
+int gvc_peer_close(gvc_ctx *ctx, void *d_ptr);
+int gvc_peer_free(gvc_ctx *ctx, void *d_ptr);
+int gvc_stage_peers(gvc_ctx *ctx, int stage, int n_peers, float *const *d_out_peers);
+
 /* Single layers on device buffers, row counts explicit (generic path; also the
  * kernel-level parity tests).  in/out are row-major n x width. */
 int gvc_graph_layer_device(gvc_ctx *ctx, const float *d_in, int width, float *d_out,

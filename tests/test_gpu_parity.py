@@ -90,11 +90,14 @@ def test_forward_vs_oracle(ctx, oracle, oracle_model, maker):
 
 def test_degree_ladder_hits_every_gather_path(ctx, oracle, oracle_model):
     """Degrees around the class thresholds of the gather schedule (64: 4-lanes-per-vertex mid tasks,
-    2048: the CTA-wide ring with its warp-to-warp hand-over) and a giant of ~70 000 neighbours whose
-    ring runs many rounds on all 8 warps; shuffled adjacency so the order matters.  Bit-exact."""
+    2048: the CTA-wide ring with its warp-to-warp hand-over and the single-warp stage-0 chains,
+    4096: the fast-mode hub chunks, 16384: the CTA-wide stage-0 sums with their 256-neighbour blocks
+    and 7 loader warps) and a giant of ~70 000 neighbours whose ring runs many rounds on all 8 warps;
+    shuffled adjacency so the order matters.  Bit-exact."""
     rng = np.random.default_rng(11)
     n = 90_000
-    want_deg = {0: 70_001, 1: 2047, 2: 2048, 3: 2049, 4: 4097, 5: 63, 6: 64, 7: 65, 8: 511, 9: 129, 10: 1, 11: 8191}
+    want_deg = {0: 70_001, 1: 2047, 2: 2048, 3: 2049, 4: 4097, 5: 63, 6: 64, 7: 65, 8: 511, 9: 129, 10: 1, 11: 8191,
+                12: 4096, 13: 8192, 14: 16_383, 15: 16_384, 16: 16_385, 17: 16_384 + 7 * 256, 18: 16_384 + 255}
     eu, ev = [], []
     for u, d in want_deg.items():
         nb = rng.choice(np.arange(100, n), size=d, replace=False)

@@ -66,6 +66,19 @@ def run_layout(layout, g0, x0, s, layers, rank, world, local, dev):
             gdist.sharded_forward(ctx.stage_device, shard, x, h1, h2, sc, s, mode)
             full = gdist.gather_scores(sc, bounds)
         torch.cuda.synchronize()
+        # the same with the rows delivered by the stage kernels themselves (peer memory) -- twice,
+        # the second pass overwrites buffers the first one filled
+        pr = gdist.PeerRows(ctx, g.n)
+        sc2 = torch.zeros(shard.n_local, device=dev)
+        with torch.cuda.stream(ctx.torch_stream()):
+            for _ in range(2):
+                gdist.sharded_forward(ctx.stage_device, shard, x, pr.h1, pr.h2, sc2, s, mode, peer_rows=pr)
+            pr.barrier()
+        torch.cuda.synchronize()
+        live = torch.zeros(g.n, dtype=torch.bool, device=dev)
+        live[:] = (g.row_ptr[1:] - g.row_ptr[:-1]).to(dev) > 0
+        peer_ok = torch.equal(sc2, sc) and torch.equal(pr.h1[live], h1[live]) and torch.equal(pr.h2[live], h2[live])
+        pr.close()
         # single-GPU forward of the whole graph on every rank
         one = pkg.Context(local)
         one.model_upload(layers)
@@ -74,7 +87,7 @@ def run_layout(layout, g0, x0, s, layers, rank, world, local, dev):
         torch.cuda.synchronize()
         one.forward_device(x0, s, ref, mode)
         one.sync()
-        same = torch.equal(full[perm] if perm is not None else full, ref)
+        same = torch.equal(full[perm] if perm is not None else full, ref) and peer_ok
         t = torch.tensor([int(same)], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:

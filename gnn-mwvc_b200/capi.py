@@ -41,6 +41,7 @@ SIGNATURES = {
     "gvc_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gvc_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gvc_stage_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "gvc_peer_owners": (C.c_int, [C.c_void_p, C.c_int, _u32p, _i32p]),
     "gvc_forward": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, C.c_int]),
     "gvc_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]),
     "gvc_stage_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int]),
@@ -226,6 +227,13 @@ class Context:
         """Mirror the output rows of `stage` (0 or 1) into these mapped buffers of the other ranks."""
         arr = (C.c_void_p * max(len(ptrs), 1))(*ptrs)
         self._check(self.lib.gvc_stage_peers(self.h, stage, len(ptrs), arr))
+
+    def peer_owners(self, bounds, peer_of_part):
+        """Vertex ranges of the parts and, per part, the index of its owner in the stage_peers tables
+        (-1: this rank): rows then only travel to the peers that own a neighbour."""
+        b = np.ascontiguousarray(bounds, np.uint32)
+        q = np.ascontiguousarray(peer_of_part, np.int32)
+        self._check(self.lib.gvc_peer_owners(self.h, len(q), _ptr(b, _u32p), q.ctypes.data_as(_i32p)))
 
     # -- forward ---------------------------------------------------------------
     def forward(self, x, weight_scale: float, mode: int = MODE_EXACT) -> np.ndarray:

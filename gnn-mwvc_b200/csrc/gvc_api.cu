@@ -137,6 +137,9 @@ struct gvc_ctx {
     DevBuf<uint32_t> d_hub_count;
     gvc::Schedule sched{};
     gvc::PeerOut peers[2] = {};          // stage 0 / stage 1 outputs mirrored into the other ranks' buffers
+    gvc::PartMap parts{};                // gvc_peer_owners: who owns which vertex range (n_parts == 0: not told)
+    DevBuf<uint8_t> d_peer_mask;         // per local vertex: the peers that read its row
+    bool have_peer_mask = false;
     uint32_t n_live = 0;                 // positions of `order` with a non-empty adjacency list
     int num_sms = 148;
     int ctas_per_sm[3] = {1, 1, 1};      // resident CTAs per SM of each stage kernel (occupancy query)
@@ -304,6 +307,7 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     PeerOut peers{};
     if (STAGE < 2) peers = c->peers[STAGE];
     peers.n_live = c->n_live;
+    peers.mask = c->have_peer_mask ? c->d_peer_mask.p - c->v_begin : nullptr;
     const int hk = STAGE == 0 ? 1 : 0;
     const uint32_t n_split = STAGE == 0 ? sc.n_giant1 : sc.n_ring;
     HubSplit hub{c->d_hub_chunk[hk].p, c->d_hub_info[hk].p, c->d_hub_partial[hk].p,
@@ -360,6 +364,24 @@ __global__ void check_col_kernel(const uint32_t *__restrict__ col, uint64_t nnz,
     }
     if (blockIdx.x == 0 && threadIdx.x < (nnz & 3)) bad |= col[n4 * 4 + threadIdx.x] >= n_global;
     if (bad) atomicOr(flag, kBadCol);
+}
+
+// Per-vertex list of the peers that read its row (gvc_peer_owners), rebuilt with every graph.
+int build_peer_mask(gvc_ctx *c) {
+    c->have_peer_mask = false;
+    const uint32_t nl = c->n_local();
+    const PartMap &pm = c->parts;
+    if (!pm.n_parts || !nl || pm.bounds[pm.n_parts] != c->n_global) return 0;
+    int rc;
+    if ((rc = c->d_peer_mask.reserve(nl))) return rc;
+    uint32_t all = 0;
+    for (int k = 0; k < pm.n_parts; ++k)
+        if (pm.peer_of_part[k] >= 0) all |= 1u << pm.peer_of_part[k];
+    peer_mask_kernel<<<std::min<unsigned>(1184, (nl + 255) / 256), 256, 0, c->stream>>>(c->row_ptr, c->col, nl, pm, all, c->d_peer_mask.p);
+    GVC_CUDA(cudaGetLastError());
+    c->launches++;
+    c->have_peer_mask = true;
+    return 0;
 }
 
 // Degree schedule of the shard's vertices (see gvc_kernels.cuh).  Part of the graph upload:
@@ -425,7 +447,7 @@ int build_schedule(gvc_ctx *c) {
     GVC_CUDA(cudaStreamSynchronize(c->stream));   // `start` and `n_chunks` live on this stack frame
     sc.n_chunks16 = n_chunks[0];
     sc.n_chunks1 = n_chunks[1];
-    return 0;
+    return build_peer_mask(c);
 }
 
 template <int STAGE>
@@ -581,6 +603,7 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     c->d_row_ptr64.release(); c->d_flag.release();
     c->stg_row_ptr.release(); c->stg_col.release(); c->stg_W.release(); c->stg_NW.release();
     c->d_order.release(); c->d_vrec.release(); c->d_bins.release(); c->d_sync.release(); c->d_feat.release();
+    c->d_peer_mask.release();
     for (int k = 0; k < 2; ++k) { c->d_hub_chunk[k].release(); c->d_hub_info[k].release(); c->d_hub_partial[k].release(); }
     c->d_hub_count.release();
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
@@ -825,6 +848,28 @@ int gvc_stage_peers(gvc_ctx *c, int stage, int n_peers, float *const *d_out_peer
     po.n = n_peers;
     c->peers[stage] = po;
     return 0;
+}
+
+int gvc_peer_owners(gvc_ctx *c, int n_parts, const uint32_t *bounds, const int *peer_of_part) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (n_parts == 0) { c->parts = PartMap{}; c->have_peer_mask = false; return 0; }
+    if (n_parts < 0 || n_parts > kMaxPeers + 1) return fail(GVC_ERR_UNSUPPORTED, "%d parts; at most %d", n_parts, kMaxPeers + 1);
+    if (!bounds || !peer_of_part) return fail(GVC_ERR_ARG, "null argument");
+    PartMap pm{};
+    pm.n_parts = n_parts;
+    for (int k = 0; k <= n_parts; ++k) {
+        if (k && bounds[k] < bounds[k - 1]) return fail(GVC_ERR_ARG, "bounds not ascending");
+        pm.bounds[k] = bounds[k];
+    }
+    for (int k = 0; k < n_parts; ++k) {
+        if (peer_of_part[k] < -1 || peer_of_part[k] >= kMaxPeers) return fail(GVC_ERR_ARG, "peer index %d out of range", peer_of_part[k]);
+        pm.peer_of_part[k] = peer_of_part[k];
+    }
+    c->parts = pm;
+    if (!c->have_graph) return 0;
+    if ((rc = use_device(c))) return rc;
+    return build_peer_mask(c);
 }
 
 int gvc_stage_device(gvc_ctx *c, int stage, const float *d_in, float *d_out, float scale, int mode) {

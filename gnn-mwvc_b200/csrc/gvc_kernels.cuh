@@ -126,6 +126,8 @@ constexpr uint32_t kChunk1 = GVC_CHUNK1;
 constexpr int kMaxPeers = 7;
 struct PeerOut {
     float *p[kMaxPeers];
+    const uint8_t *mask;    // indexed by GLOBAL vertex id (pointer pre-offset by -v_begin): bit q set = peer q owns a
+                            // neighbour of the vertex and therefore reads its row; null = every peer gets every row
     int n;                  // 0: single GPU, or rows exchanged by a collective instead
     uint32_t n_live;        // positions of `order` below this hold vertices with neighbours
 };
@@ -271,8 +273,10 @@ __device__ __forceinline__ void tile_linear_relu_store16(const float *__restrict
             const size_t at = (size_t)vid[i] * 16 + 4 * og;
             *reinterpret_cast<float4 *>(out + at) = o;
             if (i < live) {
+                const uint32_t m = peers.mask ? peers.mask[vid[i]] : 0xFFu;
 #pragma unroll 1
-                for (int q = 0; q < peers.n; ++q) *reinterpret_cast<float4 *>(peers.p[q] + at) = o;
+                for (int q = 0; q < peers.n; ++q)
+                    if (m >> q & 1u) *reinterpret_cast<float4 *>(peers.p[q] + at) = o;
             }
         }
     }
@@ -977,9 +981,9 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     float *P = smem;                                             // packed parameters
     constexpr int kParamFloats = (D.floats() + 3) / 4 * 4;
     float *ring_acc = smem + kParamFloats;                       // 16 sums, the CTA's ring claim [16], a chunk record [20..23],
-    PeerOut &peers = *reinterpret_cast<PeerOut *>(ring_acc + 24);   // the peer table [24..39] (shared memory: passed by reference)
-    static_assert(sizeof(PeerOut) == 64, "PeerOut is laid out in 16 floats of shared memory");
-    float *warp_mem = ring_acc + 40;
+    PeerOut &peers = *reinterpret_cast<PeerOut *>(ring_acc + 24);   // the peer table [24..43] (shared memory: passed by reference)
+    static_assert(sizeof(PeerOut) <= 80, "PeerOut is laid out in 20 floats of shared memory");
+    float *warp_mem = ring_acc + 44;
 
     for (int i = threadIdx.x; i < D.floats(); i += kCtaThreads) P[i] = __ldg(params + i);
     if (threadIdx.x == 0) peers = peers_arg;
@@ -1200,7 +1204,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
 template <int STAGE>
 constexpr size_t stage_smem_bytes() {
     constexpr StageDims D = stage_dims(STAGE);
-    return ((D.floats() + 3) / 4 * 4 + 40 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
+    return ((D.floats() + 3) / 4 * 4 + 44 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
 }
 
 // ---- schedule construction (graph upload time) -------------------------------------------
@@ -1226,6 +1230,30 @@ __global__ void degree_scatter_kernel(const uint32_t *__restrict__ row_ptr, cons
         const uint32_t pos = atomicAdd(&cursor[degree_bin(end - beg)], 1u);
         order[pos] = u;
         vrec[pos] = make_uint4(u, beg, end, Wv[u]);      // everything a tile needs about the vertex, 16 B
+    }
+}
+
+// Which peers read the row of local vertex u?  Those that own one of its neighbours (the adjacency
+// is symmetric).  bounds[0..n_parts] are the vertex ranges of the parts, peer_of_part[k] the index
+// of part k's owner in the peer tables (-1: this rank).  One thread per vertex; a hub is done as
+// soon as every peer has been seen.
+struct PartMap {
+    uint32_t bounds[kMaxPeers + 2];
+    int peer_of_part[kMaxPeers + 1];
+    int n_parts;
+};
+__global__ void peer_mask_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                                 uint32_t n_local, const PartMap pm, uint32_t all_peers, uint8_t *__restrict__ mask) {
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_local; u += gridDim.x * blockDim.x) {
+        uint32_t m = 0;
+        for (uint32_t e = row_ptr[u], end = row_ptr[u + 1]; e < end && m != all_peers; ++e) {
+            const uint32_t v = col[e];
+            int k = 0;
+            while (k + 1 < pm.n_parts && v >= pm.bounds[k + 1]) ++k;
+            const int q = pm.peer_of_part[k];
+            if (q >= 0) m |= 1u << q;
+        }
+        mask[u] = (uint8_t)m;
     }
 }
 
@@ -1304,8 +1332,10 @@ stage_tail_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restri
         if (lane < 16) {
             const float o = relu_ref(__fadd_rn(dot2(f[0], Wc, D.Kc, 16, lane), bc[lane]));
             out[(size_t)(v_begin + ul) * 16 + lane] = o;
+            const uint32_t m = peers.mask ? peers.mask[v_begin + ul] : 0xFFu;
             if (end > beg)
-                for (int q = 0; q < peers.n; ++q) peers.p[q][(size_t)(v_begin + ul) * 16 + lane] = o;
+                for (int q = 0; q < peers.n; ++q)
+                    if (m >> q & 1u) peers.p[q][(size_t)(v_begin + ul) * 16 + lane] = o;
         }
     } else {
         if (lane == 0) {   // 1 row x 1 column kernel: four accumulators, (c0+c1)+(c2+c3)

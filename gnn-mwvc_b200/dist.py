@@ -86,7 +86,9 @@ class PeerRows:
     ranks' copies (``gvc_stage_peers``), so the exchange between two stages shrinks to a barrier.
     One process per GPU, at most 8 ranks, NCCL group for the handle exchange and the barrier."""
 
-    def __init__(self, ctx, n_global: int, group=None):
+    def __init__(self, ctx, n_global: int, group=None, bounds=None):
+        """bounds (the vertex ranges of all ranks, as in Shard.bounds): when given, a row only
+        travels to the ranks that own a neighbour of its vertex instead of to all of them."""
         self.ctx, self.group = ctx, group
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         dev = torch.device("cuda", ctx.device)
@@ -108,6 +110,8 @@ class PeerRows:
                 self.mapped[k].append(ctx.peer_open(hb[64 * k:64 * (k + 1)]))
         ctx.stage_peers(0, self.mapped[0])
         ctx.stage_peers(1, self.mapped[1])
+        if bounds is not None:
+            ctx.peer_owners(bounds, [-1 if r == rank else (r if r < rank else r - 1) for r in range(world)])
         self.h1 = _as_tensor(self.own[0], (int(n_global), 16), dev)
         self.h2 = _as_tensor(self.own[1], (int(n_global), 16), dev)
         self._token = torch.zeros(1, device=dev)
@@ -120,6 +124,7 @@ class PeerRows:
     def close(self) -> None:
         self.ctx.stage_peers(0, [])
         self.ctx.stage_peers(1, [])
+        self.ctx.peer_owners([0], [])
         torch.cuda.synchronize()
         dist.barrier(self.group)                 # nobody still writes into a buffer that is about to go
         for k in range(2):

@@ -168,6 +168,12 @@ int gvc_peer_open(gvc_ctx *ctx, const unsigned char *handle, void **d_ptr);
 int gvc_peer_close(gvc_ctx *ctx, void *d_ptr);
 int gvc_peer_free(gvc_ctx *ctx, void *d_ptr);
 int gvc_stage_peers(gvc_ctx *ctx, int stage, int n_peers, float *const *d_out_peers);
+/* Optional: tell the context which rank owns which vertex range -- bounds[0..n_parts] ascending,
+ * bounds[n_parts] == n_global; peer_of_part[k] = position of part k's owner in the tables given to
+ * gvc_stage_peers, -1 for this rank's own part.  A row then only goes to the peers that own a
+ * neighbour of its vertex (the adjacency is symmetric: nobody else reads it) instead of to all of
+ * them.  The per-vertex peer lists are rebuilt with every graph upload; n_parts = 0 forgets them. */
+int gvc_peer_owners(gvc_ctx *ctx, int n_parts, const uint32_t *bounds, const int *peer_of_part);
 
 /* Single layers on device buffers, row counts explicit (generic path; also the
  * kernel-level parity tests).  in/out are row-major n x width. */

@@ -247,6 +247,62 @@ def test_relabelled_shards_are_bit_identical(ctx, model_layers):
             c.close()
 
 
+def test_peer_mirrored_rows_replace_the_exchange(ctx, model_layers):
+    """Multi-GPU without the collective: every shard's stage kernels also store their rows into the
+    OTHER shards' private h1/h2 copies (gvc_stage_peers; here plain device pointers on one GPU, over
+    NVLink via CUDA IPC in a real run).  Afterwards every copy holds all rows anybody can read --
+    a row only goes to the shards that own a neighbour of its vertex (gvc_peer_owners) -- and the
+    scores equal the single-shard ones bit for bit."""
+    g0 = graphs.rmat_graph(13, 16, seed=63, n_limit=8189)
+    rp0, col0, W0, NW0, x0, s = inputs_of(g0)
+    ctx.graph_upload(rp0, col0, W0, NW0)
+    want = ctx.forward(x0, s)
+    dev = torch.device("cuda:0")
+    parts = 3
+    g, perm = graphs.balanced_relabel(g0, parts)
+    rp, col, W, NW, x, _ = inputs_of(g, s)
+    per = g.n // parts
+    tail = int(perm[g0.n - 1])
+    dx = torch.from_numpy(x).to(dev)
+    h1 = [torch.full((g.n, 16), float("nan"), device=dev) for _ in range(parts)]
+    h2 = [torch.full((g.n, 16), float("nan"), device=dev) for _ in range(parts)]
+    out = torch.empty(g.n, device=dev)
+    shards = []
+    for p in range(parts):
+        a, b = p * per, (p + 1) * per
+        c = pkg.Context(0)
+        c.model_upload(model_layers)
+        c.graph_upload(rp[a:b + 1] - rp[a], col[int(rp[a]):int(rp[b])], W[a:b], NW[a:b], n_global=g.n, v_begin=a, v_end=b)
+        c.graph_set_tail(tail)
+        c.stage_peers(0, [h1[q].data_ptr() for q in range(parts) if q != p])
+        c.stage_peers(1, [h2[q].data_ptr() for q in range(parts) if q != p])
+        c.peer_owners([q * per for q in range(parts + 1)], [-1 if q == p else (q if q < p else q - 1) for q in range(parts)])
+        shards.append(c)
+    torch.cuda.synchronize()
+    for mode in (pkg.MODE_EXACT, pkg.MODE_FAST):
+        for stage in range(3):
+            for p, c in enumerate(shards):
+                src = (dx, h1[p], h2[p])[stage]
+                dst = (h1[p], h2[p], out[p * per:(p + 1) * per])[stage]
+                c.stage_device(stage, src, dst, s, mode)
+            for c in shards:
+                c.sync()                                  # the barrier between two stages
+        got = out.cpu().numpy()[perm.numpy()]
+        if mode == pkg.MODE_EXACT:
+            assert_bit_equal(got, want, "peer-mirrored rows")
+        else:
+            assert_rel_close(got, want, FAST_RTOL, "peer-mirrored rows, fast")
+    src = np.repeat(np.arange(g.n), np.diff(rp.astype(np.int64)))
+    for p in range(parts):
+        missing = torch.isnan(h1[p]).any(1).cpu().numpy()
+        own = np.zeros(g.n, bool); own[p * per:(p + 1) * per] = True
+        read = np.zeros(g.n, bool); read[col[own[src]]] = True      # what shard p gathers: its vertices' neighbours
+        assert not missing[read | own].any()                  # every row shard p reads arrived in its copy
+        assert missing[~read & ~own].all()                    # and nothing else travelled
+    for c in shards:
+        c.close()
+
+
 def test_generic_path_any_layer_sequence(oracle):
     """operator>> accepts any sequence of the four layer kinds; non-GNN_VC models run on
     the per-layer kernels (SURVEY.md 8(b) genericity)."""

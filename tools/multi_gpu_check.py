@@ -68,7 +68,7 @@ def run_layout(layout, g0, x0, s, layers, rank, world, local, dev):
         torch.cuda.synchronize()
         # the same with the rows delivered by the stage kernels themselves (peer memory) -- twice,
         # the second pass overwrites buffers the first one filled
-        pr = gdist.PeerRows(ctx, g.n)
+        pr = gdist.PeerRows(ctx, g.n, bounds=bounds if layout == "balanced" else None)
         sc2 = torch.zeros(shard.n_local, device=dev)
         with torch.cuda.stream(ctx.torch_stream()):
             for _ in range(2):
@@ -77,6 +77,10 @@ def run_layout(layout, g0, x0, s, layers, rank, world, local, dev):
         torch.cuda.synchronize()
         live = torch.zeros(g.n, dtype=torch.bool, device=dev)
         live[:] = (g.row_ptr[1:] - g.row_ptr[:-1]).to(dev) > 0
+        if layout == "balanced":      # rows only travel to the ranks that read them: compare what this rank reads
+            live[:] = False
+            live[shard.col.to(torch.int64) & 0xFFFFFFFF] = True
+            live[shard.v_begin:shard.v_end] = True
         peer_ok = torch.equal(sc2, sc) and torch.equal(pr.h1[live], h1[live]) and torch.equal(pr.h2[live], h2[live])
         pr.close()
         # single-GPU forward of the whole graph on every rank

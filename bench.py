@@ -268,7 +268,13 @@ def run_ours(args):
     stream = ctx.torch_stream()
     # N > 1: the stage kernels store their rows straight into the other ranks' h1/h2 over NVLink
     # (peer memory); --exchange nccl all-gathers them between the stages instead
-    pr = gdist.PeerRows(ctx, g.n, bounds=bounds) if world > 1 and args.exchange == "peer" else None
+    pr, pr_note = None, None
+    if world > 1 and args.exchange == "peer":
+        try:
+            pr = gdist.PeerRows(ctx, g.n, bounds=bounds)
+        except RuntimeError as e:          # raised on every rank alike: fall back to the collective, and say so
+            pr_note = str(e)
+            print(f"bench: {pr_note}; exchanging rows with NCCL all-gathers instead", file=sys.stderr, flush=True)
     h1 = pr.h1 if pr else torch.zeros(g.n, 16, device=dev)
     h2 = pr.h2 if pr else torch.zeros(g.n, 16, device=dev)
     scores = torch.zeros(shard.n_local, device=dev)
@@ -483,7 +489,7 @@ def run_ours(args):
             "config": {"workload": wl_name, "vertices": n, "edges": e_total, "nnz": m, "mode": args.mode,
                        "weights": "trained GNN_VC model (tests/golden/mwvc_model.npz)",
                        "l2": "256 MiB flush write between timed steps; working set (CSR + rows) also exceeds the 126 MB L2",
-                       "sharding": "single GPU" if world == 1 else f"{world} equal vertex ranges of the relabelled graph (vertices dealt to the shards by descending degree: equal counts, equal nnz), " + ("the stage kernels store every 16-float row into the h buffers of the ranks that own a neighbour of its vertex, over NVLink (CUDA IPC peer memory), a one-element NCCL all-reduce as barrier after stages 0 and 1" if pr else "NCCL all-gather of the 16-float rows of the non-isolated vertices after stages 0 and 1"),
+                       "sharding": "single GPU" if world == 1 else f"{world} equal vertex ranges of the relabelled graph (vertices dealt to the shards by descending degree: equal counts, equal nnz), " + ("the stage kernels store every 16-float row into the h buffers of the ranks that own a neighbour of its vertex, over NVLink (CUDA IPC peer memory), a one-element NCCL all-reduce as barrier after stages 0 and 1" if pr else "NCCL all-gather of the 16-float rows of the non-isolated vertices after stages 0 and 1" + (f" [{pr_note}]" if pr_note else "")),
                        "graph_generation_s": round(gen_s, 2)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "phase_ms": phase_ms, "other_mode": other,

@@ -88,26 +88,47 @@ class PeerRows:
 
     def __init__(self, ctx, n_global: int, group=None, bounds=None):
         """bounds (the vertex ranges of all ranks, as in Shard.bounds): when given, a row only
-        travels to the ranks that own a neighbour of its vertex instead of to all of them."""
+        travels to the ranks that own a neighbour of its vertex instead of to all of them.
+        Collective: every rank of the group must call it.  Raises RuntimeError on EVERY rank if
+        any rank could not allocate or map the buffers (the ranks agree before they go on, so a
+        caller can fall back to exchange_rows without hanging anybody)."""
         self.ctx, self.group = ctx, group
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         dev = torch.device("cuda", ctx.device)
         nbytes = int(n_global) * 16 * 4
-        self.own, handles = [], b""
-        for _ in range(2):
-            ptr, h = ctx.peer_alloc(nbytes)
-            self.own.append(ptr)
-            handles += h
+        self.own, self.mapped, handles, err = [], [[], []], b"", None
+
+        def agree(what):
+            ok = torch.tensor([0 if err else 1], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self._abandon()
+                raise RuntimeError(f"peer memory unavailable ({what}): {err or 'another rank failed'}")
+
+        try:
+            if world - 1 > 7:
+                raise RuntimeError(f"{world} ranks; the stage kernels mirror into at most 7 peers")
+            for _ in range(2):
+                ptr, h = ctx.peer_alloc(nbytes)
+                self.own.append(ptr)
+                handles += h
+        except Exception as e:           # noqa: BLE001 -- reported on every rank below
+            err = e
+            handles = bytes(128)
+        agree("allocation")
         mine = torch.tensor(list(handles), dtype=torch.uint8, device=dev)
         everybody = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(everybody, mine, group=group)
-        self.mapped = [[], []]
-        for r in range(world):
-            if r == rank:
-                continue
-            hb = bytes(everybody[r].cpu().tolist())
-            for k in range(2):
-                self.mapped[k].append(ctx.peer_open(hb[64 * k:64 * (k + 1)]))
+        try:
+            for r in range(world):
+                if r == rank:
+                    continue
+                hb = bytes(everybody[r].cpu().tolist())
+                for k in range(2):
+                    self.mapped[k].append(ctx.peer_open(hb[64 * k:64 * (k + 1)]))
+        except Exception as e:           # noqa: BLE001
+            err = e
+        agree("mapping the other ranks' buffers")
         ctx.stage_peers(0, self.mapped[0])
         ctx.stage_peers(1, self.mapped[1])
         if bounds is not None:
@@ -115,6 +136,21 @@ class PeerRows:
         self.h1 = _as_tensor(self.own[0], (int(n_global), 16), dev)
         self.h2 = _as_tensor(self.own[1], (int(n_global), 16), dev)
         self._token = torch.zeros(1, device=dev)
+
+    def _abandon(self) -> None:
+        """Give back what this rank got when the set-up failed somewhere (no collectives)."""
+        for k in range(2):
+            for p in self.mapped[k]:
+                try:
+                    self.ctx.peer_close(p)
+                except Exception:        # noqa: BLE001
+                    pass
+        for p in self.own:
+            try:
+                self.ctx.peer_free(p)
+            except Exception:            # noqa: BLE001
+                pass
+        self.own, self.mapped = [], [[], []]
 
     def barrier(self) -> None:
         """Every rank's stage kernel (and with it its stores into our buffers) has finished: a

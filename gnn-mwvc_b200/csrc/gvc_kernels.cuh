@@ -25,12 +25,17 @@
 // vertices, 80 % of the adjacency in vertices of degree >= 64, one vertex of
 // degree 64 452) and the sums are sequential per vertex, so work is organised by
 // degree (the vertices are counting-sorted by degree bin at graph upload):
-//   ring    deg >= 2048   all 8 warps of a CTA serve ONE vertex: each warp
+//   ring    deg >= 2048   exact: all 8 warps of a CTA serve ONE vertex: each warp
 //                         fetches every 8th 64-row batch, the running sum is
 //                         handed from warp to warp through named barriers, so
-//                         512 rows are in flight for a single sequential chain
+//                         1024 rows are in flight for a single sequential chain
+//                         (w=1: one warp per vertex, from 16384 neighbours on a CTA
+//                         with one chain warp and 7 loader warps).
+//                         fast: no order to keep -- the lists are cut into chunks of
+//                         4096 entries, a CTA (w=16) or warp (w=1) per chunk, the
+//                         partial sums are added in chunk order by whoever finishes last
 //   mid     64 <= deg     8 vertices per warp task, 4 lanes per vertex, 16 rows in
-//           < 2048        flight per vertex (w=1: one vertex at a time, whole warp)
+//           < 2048        flight per vertex (w=1: one lane per vertex, as in tiles)
 //   tile    deg < 64      32 vertices per warp, 4 lanes per vertex (1 for w=1)
 // ring and mid tasks only produce the 32-float feature vector (side buffer,
 // 128 B per vertex); "feature tiles" later run the dense chain on 32 of them, so
@@ -38,6 +43,11 @@
 // tasks form a two-ended list (heaviest gathers ... lightest tiles); half of the
 // warps of every CTA draw from the heavy end, half from the light end, so that
 // latency-bound gathers and FMA-bound dense tiles overlap on every SM.
+//
+// Several GPUs (one process each, a vertex range per GPU): the store epilogue of
+// stages 0 and 1 also writes each row into the output buffers of the ranks that
+// read it (peer memory over NVLink, PeerOut), so the row exchange between two
+// stages happens inside the kernel and only a barrier remains between launches.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -995,8 +1005,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     uint32_t *ready = sync + kSyncCounters;
 
     // ---- ring tasks (width 16 only): the whole CTA, largest vertices first --------------------
-    // With w = 1 the chain costs the same 4 cycles per neighbour whoever feeds it and one warp
-    // can keep its own loads ahead, so stage 0 runs the giants as single-warp tasks instead.
+    // (stage 0 runs its giants below 16384 neighbours as single-warp tasks of the queue instead)
     if constexpr (STAGE == 0 && EXACT) {
         // stage 0, exact mode: the few vertices whose sequential sum is long enough to be the
         // critical path of the stage get a whole CTA (ring_gather1_exact), largest first
@@ -1100,7 +1109,8 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     }
 
     // ---- dynamic tasks, one warp each ----------------------------------------------------------------
-    // stage 0: front = the giants, one warp each; everything else is a 32-vertex tile.
+    // stage 0: front = the giants (exact: those the ring phase did not take, one warp each; fast:
+    // their chunks); everything else is a 32-vertex tile.
     // stages 1/2: front = mid tasks (8 vertices each); tiles hold the vertices of degree < 64.
     const uint32_t n_pre = STAGE == 0 ? sc.n_giant1 : sc.n_ring + sc.n_mid;   // positions that go through feature tiles
     const uint32_t n_front = STAGE == 0 ? (EXACT ? sc.n_giant1 - sc.n_ring1 : sc.n_chunks1) : (sc.n_mid + 7) / 8;

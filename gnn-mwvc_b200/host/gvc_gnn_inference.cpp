@@ -17,6 +17,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <random>
 #include <algorithm>
 #include <string>
@@ -75,9 +76,21 @@ csr_view extract_csr(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g) {
     s.row_ptr[0] = 0;
     for (Tn u = 0; u < n; ++u) s.row_ptr[u + 1] += s.row_ptr[u];
     s.nnz = s.row_ptr[n];
-    // now that nnz is known: the adjacency buffer (the per-vertex ones are big enough and stay)
-    rc = gvc_graph_staging(ctx, n, s.nnz, &s.row_ptr, &s.col, &s.w, &s.nw);
-    if (rc != 0) gvc_host::die("gvc_graph_staging", rc);
+    // now that nnz is known: the adjacency buffer (the per-vertex ones are big enough and stay).
+    // Pinning host memory costs about 0.5 ms per MB once; for a very large first graph that is more
+    // than the faster copies win back (GNN_VC's later graphs are much smaller), and pinning several
+    // GB can fail: above GVC_STAGING_MAX_MB (default 256) the ids go through ordinary memory, which
+    // gvc_graph_upload takes just as well.
+    static const uint64_t staging_max = [] {
+        const char *e = std::getenv("GVC_STAGING_MAX_MB");
+        return (uint64_t)(e ? std::strtoull(e, nullptr, 10) : 256) << 20;
+    }();
+    static std::vector<uint32_t> pageable_col;
+    rc = s.nnz * sizeof(uint32_t) <= staging_max ? gvc_graph_staging(ctx, n, s.nnz, &s.row_ptr, &s.col, &s.w, &s.nw) : -1;
+    if (rc != 0) {
+        if (pageable_col.size() < s.nnz) pageable_col.resize(s.nnz);
+        s.col = pageable_col.data();
+    }
     for_ranges([&](Tn a, Tn b) {
         for (Tn u = a; u < b; ++u) std::copy(g.begin(u), g.end(u), s.col + s.row_ptr[u]);
     });

@@ -159,7 +159,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -211,7 +211,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
+    os.environ["NCCL_DEBUG"] = "WARN"      # warnings only (they go to stderr with everything else, see own_stdout)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
@@ -495,11 +495,32 @@ def run_ours(args):
             "roofline": roof, "cpu_baseline": cpu, "phase_ms": phase_ms, "other_mode": other,
             "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = None
+
+
+def own_stdout():
+    """ONE JSON line on stdout is the contract, and libraries print there too (NCCL's version
+    banner, for one): keep the real stdout for emit(), send everything else to stderr."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -516,6 +537,7 @@ def main():
                     help="N > 1: rows delivered by the stage kernels through peer memory, or NCCL all-gathers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    own_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -439,14 +439,15 @@ int build_schedule(gvc_ctx *c) {
         if ((rc = c->d_hub_info[k].reserve(n_class[k]))) return rc;
         if ((rc = c->d_hub_partial[k].reserve(bound * (k == 0 ? 16 : 1)))) return rc;
         hub_chunks_kernel<<<std::min<unsigned>(1184, (n_class[k] + 255) / 256), 256, 0, c->stream>>>(
-            c->d_vrec.p, n_class[k], chunk_len[k], c->d_hub_count.p + k, c->d_hub_info[k].p, c->d_hub_chunk[k].p);
+            c->d_vrec.p, n_class[k], chunk_len[k], c->d_hub_count.p + k, c->d_hub_info[k].p, c->d_hub_chunk[k].p,
+            (uint32_t)std::min<size_t>(bound, 0xFFFFFFFFu));
         GVC_CUDA(cudaGetLastError());
         c->launches++;
     }
     GVC_CUDA(cudaMemcpyAsync(n_chunks, c->d_hub_count.p, sizeof(n_chunks), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));   // `start` and `n_chunks` live on this stack frame
-    sc.n_chunks16 = n_chunks[0];
-    sc.n_chunks1 = n_chunks[1];
+    sc.n_chunks16 = (uint32_t)std::min<uint64_t>(n_chunks[0], c->nnz / kChunk16 + n_ring);
+    sc.n_chunks1 = (uint32_t)std::min<uint64_t>(n_chunks[1], c->nnz / kChunk1 + n_giant1);
     return build_peer_mask(c);
 }
 
@@ -702,7 +703,16 @@ int gvc_graph_upload_shard(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
         GVC_CUDA(cudaGetLastError());
         c->launches++;
     }
+    // the schedule is built from the offsets: they must be known good first (a negative "degree"
+    // would send the chunk builder past its buffers); the id check may still be running
+    uint32_t flag = 0;
+    GVC_CUDA(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
     tr.tick("upload: narrow offsets");
+    if (flag & kBadRowPtr) {
+        cudaStreamSynchronize(c->copy_stream);
+        return fail(GVC_ERR_ARG, "row_ptr is not monotone or exceeds row_ptr[n]");
+    }
     if ((rc = set_graph_views(c, n_global, v_begin, v_end, c->own_row_ptr.p, c->own_col.p, c->own_W.p, c->own_NW.p, nnz))) {
         cudaStreamSynchronize(c->copy_stream);
         c->have_graph = false;
@@ -710,12 +720,10 @@ int gvc_graph_upload_shard(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
     }
     tr.tick("upload: schedule");
     GVC_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));           // forwards start after the adjacency landed
-    uint32_t flag = 0;
     GVC_CUDA(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));                        // also: the caller's buffers are free again
     if (flag) {
         c->have_graph = false;
-        if (flag & kBadRowPtr) return fail(GVC_ERR_ARG, "row_ptr is not monotone or exceeds row_ptr[n]");
         return fail(GVC_ERR_ARG, "a neighbour id is >= %u vertices", n_global);
     }
     return 0;

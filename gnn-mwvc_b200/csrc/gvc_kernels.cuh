@@ -1270,13 +1270,15 @@ __global__ void peer_mask_kernel(const uint32_t *__restrict__ row_ptr, const uin
 // fast-mode hub chunks of order[0, n_class): see HubSplit.  counter[0] ends up as the number of chunks.
 __global__ void hub_chunks_kernel(const uint4 *__restrict__ vrec, uint32_t n_class, uint32_t chunk_len,
                                   uint32_t *__restrict__ counter, uint2 *__restrict__ info,
-                                  uint4 *__restrict__ chunk) {
+                                  uint4 *__restrict__ chunk, uint32_t capacity /* entries of `chunk` */) {
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_class; g += gridDim.x * blockDim.x) {
         const uint4 r = vrec[g];
         const uint32_t nch = max(1u, (r.z - r.y + chunk_len - 1) / chunk_len);
         const uint32_t base = atomicAdd(counter, nch);
         info[g] = make_uint2(base, nch);
-        for (uint32_t c = 0; c < nch; ++c)
+        // (capacity = nnz / chunk_len + n_class covers every consistent CSR; the check keeps offsets
+        // a caller adopted without validation from writing past the list)
+        for (uint32_t c = 0; c < nch && base + c < capacity; ++c)
             chunk[base + c] = make_uint4(g, r.y + c * chunk_len, min(r.z, r.y + (c + 1) * chunk_len), c);
     }
 }

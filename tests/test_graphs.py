@@ -92,6 +92,20 @@ def test_relabel_keeps_lists_and_balances(fn):
         assert max(shard_nnz) > 1.5 * min(shard_nnz)      # R-MAT: ids with zero low bits are the heavy ones
 
 
+def test_live_rows_are_the_non_isolated_prefix():
+    g = graphs.rmat_graph(11, 8, seed=3)
+    h, _ = graphs.balanced_relabel(g, 4)
+    per = h.n // 4
+    bounds = [r * per for r in range(5)]
+    live = graphs.live_rows(h.row_ptr, bounds)
+    deg = (h.row_ptr[1:] - h.row_ptr[:-1]).numpy()
+    for r in range(4):
+        d = deg[bounds[r]:bounds[r + 1]]
+        assert (d[:live[r]] > 0).all() and (d[live[r]:] == 0).all()     # sorted by degree: live rows are a prefix
+    assert max(live) - min(live) <= 1 and 0 < max(live) < per
+    assert graphs.live_rows(torch.zeros(9, dtype=torch.int64), [0, 4, 8]) == [0, 0]
+
+
 def test_u32_bit_patterns():
     t = torch.tensor([0, 1, 2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1])
     assert graphs.to_u32(t).numpy().view(np.uint32).tolist() == t.tolist()

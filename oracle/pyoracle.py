@@ -161,10 +161,23 @@ class Oracle:
         return out
 
 
+DROPIN_SO = HERE / "_ref" / "libgnndropin.so"
+
+
+def build_dropin_harness() -> Path | None:
+    """oracle/_ref/libgnndropin.so: ref_harness.cpp over the drop-in host units (needs /root/reference
+    for the headers and gnn-mwvc_b200/libgvc.so)."""
+    if not Path("/root/reference/include/gnn_inference.hpp").exists():
+        return DROPIN_SO if DROPIN_SO.exists() else None
+    subprocess.check_call(["make", "-s", "-C", str(HERE), "dropin_harness"])
+    return DROPIN_SO
+
+
 class Reference:
     """The unmodified reference (OpenBLAS kernel pinned to Prescott)."""
 
-    def __init__(self, threads: int | None = None):
+    def __init__(self, threads: int | None = None, so: Path | None = None):
+        REF_SO = so or globals()["REF_SO"]
         if not REF_SO.exists():
             raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
         # must be set before libopenblas' constructor runs

@@ -24,10 +24,21 @@
 #include <utility>
 #include <vector>
 
+#ifdef GVC_HARNESS_DROPIN
+// The same harness over the DROP-IN host units (gnn-mwvc_b200/host/*.cpp + libgvc) instead of the
+// reference's src/*.cpp: `make dropin_harness`.  Lets the tests call the replacement through the
+// reference's own C++ interface (parse, print, constructors on the CPU; forward on a GPU).
+static void openblas_set_num_threads(int) {}
+static char *openblas_get_config(void) {
+    static char s[] = "drop-in host units over libgvc (no BLAS)";
+    return s;
+}
+#else
 extern "C" {
 void openblas_set_num_threads(int n);
 char *openblas_get_config(void);
 }
+#endif
 
 namespace {
 struct ref_state {

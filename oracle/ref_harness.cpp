@@ -169,4 +169,82 @@ void ref_linear_init(int K, int Nout, size_t seed, float *out) {
     std::copy(l.bias.raw().begin(), l.bias.raw().end(), out + (size_t)K * Nout);
 }
 
+// class matrix (include/matrix.hpp, src/matrix.cpp:8-104) exercised through its public interface
+// only: construction, element access, the stateful row selection of operator[] / raw(), the
+// iterator pairs, the three kinds of resize, and the text form both ways.  Every observation is
+// appended to `out` (as floats) and the text forms to `text`; the test runs this once over the
+// reference's matrix.cpp and once over the drop-in's and compares the two records.
+size_t ref_matrix_probe(float *out, size_t cap, char *text, size_t text_cap) {
+    std::vector<float> o;
+    std::ostringstream all;
+    auto dump = [&](matrix &m) {
+        o.push_back((float)m.get_height());
+        o.push_back((float)m.get_width());
+        matrix &r = m.raw();
+        o.push_back((float)(r.end() - r.begin()));
+        for (auto it = r.begin(); it != r.end(); ++it) o.push_back(*it);
+    };
+    matrix e;
+    dump(e);
+    matrix a(3, 4);
+    dump(a);                                             // initial contents
+    for (size_t i = 0; i < 3; ++i)
+        for (size_t j = 0; j < 4; ++j) a(i, j) = (float)(10 * i + j) + 0.5f;
+    dump(a);
+    // row selection: a[i] narrows begin()/end() to row i until raw() is called
+    for (size_t i = 0; i < 3; ++i) {
+        matrix &row = a[i];
+        o.push_back((float)(row.end() - row.begin()));
+        for (auto it = row.begin(); it != row.end(); ++it) o.push_back(*it);
+        o.push_back((float)row.get_height());
+        o.push_back((float)row.get_width());
+    }
+    a[2];
+    o.push_back((float)(a.end() - a.begin()));           // still selected?
+    o.push_back(*a.begin());
+    a.raw();
+    o.push_back((float)(a.end() - a.begin()));
+    for (size_t i = 0; i < 3; ++i) {
+        o.push_back((float)(a.end(i) - a.begin(i)));
+        o.push_back(*a.begin(i));
+    }
+    const matrix &ca = a;
+    o.push_back(ca(1, 2));
+    o.push_back((float)(ca.end() - ca.begin()));
+    o.push_back((float)(ca.end(1) - ca.begin(1)));
+    o.push_back((float)(ca[1].end() - ca[1].begin()));
+    ca.raw();
+    all << a << "|";                                      // text form of a whole matrix
+    a[1];
+    all << a << "|";                                      // ... and with a row selected
+    a.raw();
+    a.resize(3, 4);                                       // same shape: contents stay
+    dump(a);
+    a.resize(2, 5);
+    dump(a);
+    a.resize(4, 4);
+    dump(a);
+    a.resize(0, 7);
+    dump(a);
+    {
+        std::istringstream is("2 3\n1 2 3\n4.5 -6e-1 7\n");
+        matrix b;
+        is >> b;
+        dump(b);
+        all << b << "|";
+        std::istringstream is2("1 2 9 8 trailing");
+        is2 >> b;                                         // re-read into a used matrix
+        dump(b);
+        all << b << "|";
+    }
+    std::string t = all.str();
+    if (text && text_cap) {
+        size_t k = t.size() < text_cap - 1 ? t.size() : text_cap - 1;
+        std::memcpy(text, t.data(), k);
+        text[k] = 0;
+    }
+    for (size_t i = 0; i < o.size() && i < cap; ++i) out[i] = o[i];
+    return o.size();
+}
+
 } // extern "C"

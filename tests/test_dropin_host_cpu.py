@@ -61,3 +61,22 @@ def test_linear_layer_random_init(both, dims):
     ours.L.ref_linear_init(K, N, seed, po._p(b, po._f32p))
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))     # same mt19937 stream, weights then bias
     assert np.abs(a).max() <= 1.0 / np.sqrt(K + 1) + 1e-7
+
+
+def test_matrix_container_behaves_like_the_reference(both):
+    """class matrix through its public interface: construction, element access,
+    the stateful row selection of operator[] / raw(), iterator pairs, resize, text form both ways."""
+    import ctypes as C
+    ref, ours = both
+    got = []
+    for side in (ref, ours):
+        side.L.ref_matrix_probe.restype = C.c_size_t
+        side.L.ref_matrix_probe.argtypes = [po._f32p, C.c_size_t, C.c_char_p, C.c_size_t]
+        out = np.full(4096, np.nan, np.float32)
+        text = C.create_string_buffer(1 << 16)
+        n = side.L.ref_matrix_probe(po._p(out, po._f32p), out.size, text, len(text))
+        assert 50 < n <= out.size
+        got.append((out[:n].copy(), text.value.decode()))
+    (a, ta), (b, tb) = got
+    assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert ta == tb and ta.count("|") == 4

@@ -247,4 +247,30 @@ size_t ref_matrix_probe(float *out, size_t cap, char *text, size_t text_cap) {
     return o.size();
 }
 
+// model built in code (model(name), add_layer, the layer constructors; src/gnn_inference.cpp:54-59)
+// and printed: the programmatic half of the interface, used by the training
+// code in old_files.  Returns the length of the text.
+size_t ref_model_build_probe(char *text, size_t text_cap) {
+    gnn::model m("built_in_code");
+    m.add_layer(gnn::graph_layer());
+    m.add_layer(gnn::linear_layer(5, 3, 42));
+    m.add_layer(gnn::ReLU());
+    m.add_layer(gnn::linear_layer(3, 1, 7));
+    m.add_layer(gnn::sigmoid());
+    gnn::graph_layer g2;
+    g2.WEIGHT_SCALE = 33.0f;                               // not part of the text form
+    m.add_layer(g2);
+    m.set_weight_scale(200.0f);
+    gnn::model copy = m;                                   // value semantics of the class
+    std::ostringstream os;
+    os << m << "|" << copy << "|" << gnn::model() << "|";
+    std::string t = os.str();
+    if (text && text_cap) {
+        size_t k = t.size() < text_cap - 1 ? t.size() : text_cap - 1;
+        std::memcpy(text, t.data(), k);
+        text[k] = 0;
+    }
+    return t.size();
+}
+
 } // extern "C"

@@ -80,3 +80,19 @@ def test_matrix_container_behaves_like_the_reference(both):
     (a, ta), (b, tb) = got
     assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert ta == tb and ta.count("|") == 4
+
+
+def test_model_built_in_code_prints_like_the_reference(both):
+    """model(name), add_layer, the layer constructors, copying a model, the empty model
+     -- printed through operator<< on both sides."""
+    import ctypes as C
+    ref, ours = both
+    texts = []
+    for side in (ref, ours):
+        side.L.ref_model_build_probe.restype = C.c_size_t
+        side.L.ref_model_build_probe.argtypes = [C.c_char_p, C.c_size_t]
+        buf = C.create_string_buffer(1 << 16)
+        n = side.L.ref_model_build_probe(buf, len(buf))
+        assert 100 < n < len(buf)
+        texts.append(buf.value.decode())
+    assert texts[0] == texts[1] and texts[0].count("|") == 3 and "built_in_code" in texts[0]

@@ -94,7 +94,11 @@ class PeerRows:
         caller can fall back to exchange_rows without hanging anybody)."""
         self.ctx, self.group = ctx, group
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        dev = torch.device("cuda", ctx.device)
+        # (a context may name its own torch device and tensor wrapper: the CPU stand-in of
+        # tests/test_dist_cpu.py does, to run this protocol over gloo and shared host memory)
+        dev = ctx.torch_device() if hasattr(ctx, "torch_device") else torch.device("cuda", ctx.device)
+        self._dev = dev
+        wrap = ctx.peer_tensor if hasattr(ctx, "peer_tensor") else (lambda ptr, shape: _as_tensor(ptr, shape, dev))
         nbytes = int(n_global) * 16 * 4
         self.own, self.mapped, handles, err = [], [[], []], b"", None
 
@@ -133,8 +137,8 @@ class PeerRows:
         ctx.stage_peers(1, self.mapped[1])
         if bounds is not None:
             ctx.peer_owners(bounds, [-1 if r == rank else (r if r < rank else r - 1) for r in range(world)])
-        self.h1 = _as_tensor(self.own[0], (int(n_global), 16), dev)
-        self.h2 = _as_tensor(self.own[1], (int(n_global), 16), dev)
+        self.h1 = wrap(self.own[0], (int(n_global), 16))
+        self.h2 = wrap(self.own[1], (int(n_global), 16))
         self._token = torch.zeros(1, device=dev)
 
     def _abandon(self) -> None:
@@ -161,7 +165,8 @@ class PeerRows:
         self.ctx.stage_peers(0, [])
         self.ctx.stage_peers(1, [])
         self.ctx.peer_owners([0], [])
-        torch.cuda.synchronize()
+        if self._dev.type == "cuda":
+            torch.cuda.synchronize()
         dist.barrier(self.group)                 # nobody still writes into a buffer that is about to go
         for k in range(2):
             for p in self.mapped[k]:

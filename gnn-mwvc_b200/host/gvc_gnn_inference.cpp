@@ -50,8 +50,25 @@ struct csr_view {
 csr_view extract_csr(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g) {
     const Tn n = g.size();
     csr_view s;
-    int rc = gvc_graph_staging(ctx, n, 0, &s.row_ptr, &s.col, &s.w, &s.nw);
-    if (rc != 0) gvc_host::die("gvc_graph_staging", rc);
+    // Where the CSR is written.  From the context's pinned staging buffers the upload runs at PCIe
+    // line rate, but pinning host memory costs about 0.5 ms per MB, once -- and GNN_VC is a
+    // one-shot process whose FIRST graph is by far its largest (measured on ER 1M / 5M: 40 ms of
+    // pinning against 10 ms saved in all later uploads together).  So only graphs of up to
+    // GVC_STAGING_MAX_MB (default 8) go through the pinned buffers, larger ones through ordinary
+    // vectors, which gvc_graph_upload takes just as well; a long-lived caller raises the limit.
+    static const uint64_t staging_max = [] {
+        const char *e = std::getenv("GVC_STAGING_MAX_MB");
+        return (uint64_t)(e ? std::strtoull(e, nullptr, 10) : 8) << 20;
+    }();
+    static std::vector<uint64_t> pg_row_ptr;
+    static std::vector<uint32_t> pg_col, pg_w, pg_nw;
+    const uint64_t vertex_bytes = 16ull * ((uint64_t)n + 1);
+    bool pinned = vertex_bytes <= staging_max &&
+                  gvc_graph_staging(ctx, n, 0, &s.row_ptr, &s.col, &s.w, &s.nw) == 0;
+    if (!pinned) {
+        if (pg_row_ptr.size() < (size_t)n + 1) { pg_row_ptr.resize((size_t)n + 1); pg_w.resize(n); pg_nw.resize(n); }
+        s.row_ptr = pg_row_ptr.data(); s.w = pg_w.data(); s.nw = pg_nw.data();
+    }
     // begin(u)/end(u)/W(u)/NW(u) only read the graph, so vertex ranges can be walked by several
     // threads (never D(u) / operator[], which write a cursor)
     const unsigned hw = std::thread::hardware_concurrency();
@@ -76,20 +93,13 @@ csr_view extract_csr(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g) {
     s.row_ptr[0] = 0;
     for (Tn u = 0; u < n; ++u) s.row_ptr[u + 1] += s.row_ptr[u];
     s.nnz = s.row_ptr[n];
-    // now that nnz is known: the adjacency buffer (the per-vertex ones are big enough and stay).
-    // Pinning host memory costs about 0.5 ms per MB once; for a very large first graph that is more
-    // than the faster copies win back (GNN_VC's later graphs are much smaller), and pinning several
-    // GB can fail: above GVC_STAGING_MAX_MB (default 256) the ids go through ordinary memory, which
-    // gvc_graph_upload takes just as well.
-    static const uint64_t staging_max = [] {
-        const char *e = std::getenv("GVC_STAGING_MAX_MB");
-        return (uint64_t)(e ? std::strtoull(e, nullptr, 10) : 256) << 20;
-    }();
-    static std::vector<uint32_t> pageable_col;
-    rc = s.nnz * sizeof(uint32_t) <= staging_max ? gvc_graph_staging(ctx, n, s.nnz, &s.row_ptr, &s.col, &s.w, &s.nw) : -1;
-    if (rc != 0) {
-        if (pageable_col.size() < s.nnz) pageable_col.resize(s.nnz);
-        s.col = pageable_col.data();
+    // now that nnz is known: the adjacency buffer (pinned per-vertex buffers are big enough and stay)
+    if (pinned && vertex_bytes + s.nnz * sizeof(uint32_t) <= staging_max &&
+        gvc_graph_staging(ctx, n, s.nnz, &s.row_ptr, &s.col, &s.w, &s.nw) == 0) {
+        // s.col now points into the pinned adjacency buffer
+    } else {
+        if (pg_col.size() < s.nnz) pg_col.resize(s.nnz);
+        s.col = pg_col.data();
     }
     for_ranges([&](Tn a, Tn b) {
         for (Tn u = a; u < b; ++u) std::copy(g.begin(u), g.end(u), s.col + s.row_ptr[u]);

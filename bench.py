@@ -107,37 +107,60 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation (oracle/_ref), or the oracle port
 # ------------------------------------------------------------------------------------------
+def reference_workload(args):
+    """The graph the reference arm times: the arm's own config when one CPU step of it stays within
+    seconds (R-MAT scale <= 20, ~4 s per predict on 16 cores), else a bounded sample of the same
+    generator (scale 20 stands in for the scale-21..23 graphs of the 2/4/8-GPU runs)."""
+    import torch
+    from gnn_mwvc_b200 import graphs
+    want = args.scale if args.scale else rmat_scale_for(args.gpus)
+    scale = min(want, 20)
+    # generated where the GPU arm generates it (torch's CUDA and CPU generators draw different
+    # streams): on the GPU box both arms time the very same graph
+    g = graphs.rmat_graph(scale, 16, seed=42, device="cuda" if torch.cuda.is_available() else "cpu")
+    name = f"rmat_scale{want}_ef16"
+    sample = None if scale == want else f"R-MAT scale {scale} ef 16 (n={g.n}, E={g.n_edges}) stands in for scale {want}"
+    return g, name, sample
+
+
+def blas_kernel(ref) -> str:
+    """'OpenBLAS 0.3.15 ... Haswell MAX_THREADS=128' -> the kernel set OpenBLAS picked for this CPU."""
+    cfg = ref.blas_config().split()
+    known = [w for w in cfg if w[0].isupper() and w.isalnum() and w not in ("OpenBLAS", "DYNAMIC_ARCH", "NO_AFFINITY")]
+    return known[-1] if known else "unknown"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
     import gnn_mwvc_b200  # noqa: F401
-    from gnn_mwvc_b200 import capi, graphs
+    from gnn_mwvc_b200 import capi
     from oracle import pyoracle as po
 
     cores = os.cpu_count() or 1
     layers = capi.load_model_npz(ROOT / "tests" / "golden" / "mwvc_model.npz")
     text = po.layers_to_text(layers)
-    # bounded sample of the same workload: same generator and parameters, smaller scale
-    sample_scale = 17 if (args.steps + args.warmup) <= 40 else 15
-    g = graphs.rmat_graph(sample_scale, 16, seed=42, device="cpu")
+    g, wl_name, sample_note = reference_workload(args)
     rp, col, W, NW = g.numpy()
     eu, ev = g.edges_numpy()
     scale = 200.0
     x = W.astype(np.float32) / np.float32(scale)
     if po.REF_SO.exists():
-        ref = po.Reference(threads=cores)
+        # the TIMED reference runs the kernel set OpenBLAS itself selects on this host (the pin to
+        # "Prescott" is the checker's, see oracle/pyoracle.py), with every host thread
+        ref = po.Reference(threads=cores, coretype=None)
         h = ref.model(text)
-        kind = "reference"
+        gh = ref.graph_create(g.n, eu, ev, W)          # resident, as GNN_VC holds its graph
+        kind, kernel = "reference", blas_kernel(ref)
 
         def step():
-            ref.predict(h, g.n, eu, ev, W, x, scale)
-            return ref.last_seconds            # predict only; graph construction excluded
+            ref.predict_on(h, gh, x, scale)
+            return ref.last_seconds                    # predict() only
     else:
         orc = po.Oracle()
         h = orc.parse(text)
-        kind, cores = "port", 1
+        kind, cores, kernel = "port", 1, "plain C restatement"
 
         def step():
             t = time.perf_counter()
@@ -148,14 +171,15 @@ def run_reference(args):
     secs = [step() for _ in range(args.steps)]
     total = float(np.sum(secs))
     value = g.n_edges * args.steps / total
-    sample = f"R-MAT scale {sample_scale} ef 16 (n={g.n}, E={g.n_edges}), predict() only, {args.steps} steps"
+    sample = (sample_note or f"the whole workload graph (n={g.n}, E={g.n_edges})") + f", predict() only, {args.steps} steps"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"rmat_scale{rmat_scale_for(args.gpus)}_ef16 (timed on the bounded sample below)",
-                   "sample": sample, "mode": "reference CPU (OpenBLAS)" if kind == "reference" else "oracle port"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": wl_name, "vertices": g.n, "edges": g.n_edges, "nnz": g.nnz, "sample": sample,
+                   "mode": f"reference CPU (OpenBLAS kernel {kernel}, {cores} threads)" if kind == "reference" else "oracle port"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "blas_kernel": kernel},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -163,39 +187,56 @@ def run_reference(args):
     return 0
 
 
-def cpu_baseline_leg(layers, budget_s: float = 20.0):
-    """Rank 0, N=1: the reference CPU path on a bounded sample (~10-30 s of CPU work)."""
-    import gnn_mwvc_b200  # noqa: F401
+def cpu_baseline_leg(layers, g_cpu, budget_s: float = 25.0):
+    """Rank 0, N=1: the reference CPU path on a bounded sample of the SAME graph the GPU arm timed
+    (a few predict() calls on it, ~10-30 s of CPU work), OpenBLAS' own kernel choice, all host threads.
+    Runs in a child process: OpenBLAS fixes its kernel set when it is first loaded."""
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        np.savez(Path(td) / "g.npz", eu=g_cpu["eu"], ev=g_cpu["ev"], w=g_cpu["w"], n=g_cpu["n"])
+        code = f"""
+import sys, os, json, time
+import numpy as np
+sys.path.insert(0, {str(ROOT)!r})
+import gnn_mwvc_b200
+from gnn_mwvc_b200 import capi
+from oracle import pyoracle as po
+z = np.load({str(Path(td) / 'g.npz')!r})
+n, eu, ev, W = int(z['n']), z['eu'], z['ev'], z['w']
+layers = capi.load_model_npz({str(ROOT / 'tests' / 'golden' / 'mwvc_model.npz')!r})
+text = po.layers_to_text(layers)
+x = W.astype(np.float32) / np.float32(200.0)
+cores = os.cpu_count() or 1
+secs, t_all = [], time.perf_counter()
+if po.REF_SO.exists():
+    ref = po.Reference(threads=cores, coretype=None)
+    h = ref.model(text); gh = ref.graph_create(n, eu, ev, W)
+    kind = 'reference'; cfg = ref.blas_config()
+    while len(secs) < 2 or (time.perf_counter() - t_all < {budget_s} and len(secs) < 6):
+        ref.predict_on(h, gh, x, 200.0); secs.append(ref.last_seconds)
+else:
     from gnn_mwvc_b200 import graphs
-    from oracle import pyoracle as po
-    cores = os.cpu_count() or 1
-    text = po.layers_to_text(layers)
-    g = graphs.rmat_graph(17, 16, seed=42, device="cpu")
-    rp, col, W, NW = g.numpy()
-    scale = 200.0
-    x = W.astype(np.float32) / np.float32(scale)
-    t_all = time.perf_counter()
-    secs = []
-    if po.REF_SO.exists():
-        ref = po.Reference(threads=cores)
-        h = ref.model(text)
-        eu, ev = g.edges_numpy()
-        kind = "reference"
-        while len(secs) < 3 or (time.perf_counter() - t_all < budget_s and len(secs) < 12):
-            ref.predict(h, g.n, eu, ev, W, x, scale)
-            secs.append(ref.last_seconds)
-    else:
-        orc = po.Oracle()
-        h = orc.parse(text)
-        kind, cores = "port", 1
-        while len(secs) < 2 or (time.perf_counter() - t_all < budget_s and len(secs) < 8):
-            t = time.perf_counter()
-            orc.predict(h, rp, col, W, NW, x, scale)
-            secs.append(time.perf_counter() - t)
+    import torch
+    g = graphs.graph_from_edges(n, torch.from_numpy(eu.astype(np.int64)), torch.from_numpy(ev.astype(np.int64)), torch.from_numpy(W.astype(np.int64)))
+    rp, col, W2, NW = g.numpy()
+    orc = po.Oracle(); h = orc.parse(text); kind, cores, cfg = 'port', 1, 'plain C restatement'
+    while len(secs) < 2 or (time.perf_counter() - t_all < {budget_s} and len(secs) < 4):
+        t = time.perf_counter(); orc.predict(h, rp, col, W2, NW, x, 200.0); secs.append(time.perf_counter() - t)
+print(json.dumps(dict(secs=secs, kind=kind, cores=cores, cfg=cfg)))
+"""
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    if r.returncode != 0:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "failed", "sample": r.stderr[-300:]}
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    secs = d["secs"]
     best = float(np.median(secs[1:])) if len(secs) > 1 else secs[0]
-    return {"value": g.n_edges / best, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"R-MAT scale 17 ef 16 (n={g.n}, E={g.n_edges}), median of {len(secs) - 1} warm predict() calls, "
-                      f"{best * 1e3:.0f} ms each"}
+    e = int(len(g_cpu["eu"]))
+    cfgw = d["cfg"].split()
+    kernel = next((w for w in reversed(cfgw) if w[0].isupper() and w.isalnum() and w not in ("OpenBLAS", "DYNAMIC_ARCH", "NO_AFFINITY")), d["cfg"])
+    return {"value": e / best, "unit": UNIT, "cores": d["cores"], "kind": d["kind"], "blas_kernel": kernel,
+            "sample": f"{'R-MAT scale 20 sample of the generator' if g_cpu.get('sample') else 'the bench graph itself'} (n={g_cpu['n']}, E={e}): median of {max(len(secs) - 1, 1)} warm predict() calls "
+                      f"after one cold call, {best * 1e3:.0f} ms each"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -211,7 +252,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG"] = "WARN"      # warnings only (they go to stderr with everything else, see own_stdout)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # a caller's setting wins (the driver reads the rank count from INFO)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
@@ -257,6 +298,12 @@ def run_ours(args):
         bounds = [0, n]
     shard = gdist.make_shard(g, bounds, rank, skip_isolated=world > 1)
     rp32 = shard.row_ptr.to(torch.int32).contiguous()
+    # host copy of the edge list: predict() end to end (the drop-in builds a reduction_graph from it)
+    # and the CPU baseline leg work on the very graph the GPU arm times, when it is small enough
+    g_cpu = None
+    if world == 1 and g.eu is not None and e_total <= 40_000_000:
+        g_cpu = {"n": n, "eu": g.eu.cpu().numpy().astype(np.uint32), "ev": g.ev.cpu().numpy().astype(np.uint32),
+                 "w": g.weights.cpu().numpy().view(np.uint32).copy()}
     g.eu = g.ev = None
     gen_s = time.perf_counter() - t0
 
@@ -404,16 +451,56 @@ def run_ours(args):
             ctx.graph_upload(srp, scol, sW, sNW)
         up_s = (time.perf_counter() - t1) / k
         h2d = int(srp.nbytes + scol.nbytes + sW.nbytes + sNW.nbytes + 4 * n)
-        e2e = {"value": max(e_total, 1) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": int(4 * n), "ms_per_step": e2e_s * 1e3, "graph_upload_ms": up_s * 1e3,
-               "graph_upload_GBps": (h2d - 4 * n) / up_s / 1e9,
-               "what": "gvc_graph_upload() + gvc_forward() per step, host buffers in, host scores out: H2D of the "
-                       "whole CSR from pinned host memory + x, id/offset checks, degree schedule, 3 fused kernels, "
-                       "D2H of the scores",
-               "csr_resident": {"value": max(e_total, 1) / res_s, "unit": UNIT, "ms_per_step": res_s * 1e3,
-                                "h2d_bytes_per_step": int(4 * n), "d2h_bytes_per_step": int(4 * n),
-                                "what": "gvc_forward() only: H2D of x, 3 fused kernels, D2H of the scores; CSR uploaded once"}}
+        c_abi = {"value": max(e_total, 1) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                 "d2h_bytes_per_step": int(4 * n), "ms_per_step": e2e_s * 1e3, "graph_upload_ms": up_s * 1e3,
+                 "graph_upload_GBps": (h2d - 4 * n) / up_s / 1e9,
+                 "what": "gvc_graph_upload() + gvc_forward() per step from pre-filled pinned staging buffers: H2D of the "
+                         "packed CSR + x, id/offset checks, degree schedule, 3 fused kernels, D2H of the scores"}
+        resident = {"value": max(e_total, 1) / res_s, "unit": UNIT, "ms_per_step": res_s * 1e3,
+                    "h2d_bytes_per_step": int(4 * n), "d2h_bytes_per_step": int(4 * n),
+                    "what": "gvc_forward() only: H2D of x, 3 fused kernels, D2H of the scores; CSR uploaded once"}
         assert np.isfinite(out_host).all()
+        # (iii) THE end-to-end number: gnn::model::predict(in, out, reduction_graph) through the
+        # reference's own C++ interface (the call src/GNN_VC.cpp:192 makes), on a reduction_graph built
+        # from the same edge list: adjacency read through begin(u)/end(u)/W/NW, staged, uploaded,
+        # compacted and scheduled on the device, forward, scores back in the host matrix -- every step.
+        e2e = None
+        if g_cpu is not None:
+            from gnn_mwvc_b200 import dropin as gdrop
+            try:
+                dr = gdrop.Dropin()
+            except FileNotFoundError as ex:
+                dr = None
+                print(f"bench: {ex}", file=sys.stderr)
+            if dr is not None:
+                os.environ["GVC_MODE"] = args.mode
+                os.environ["GVC_DEVICE"] = str(local_rank)
+                dm = dr.model(gdrop.model_text(layers))
+                dg = dr.graph(n, g_cpu["eu"], g_cpu["ev"], g_cpu["w"])
+                first = None
+                for i in range(3):
+                    out_pred = dr.predict(dm, dg, x_host, weight_scale)
+                    first = first if first is not None else dr.last_seconds
+                secs = []
+                for _ in range(k):
+                    out_pred = dr.predict(dm, dg, x_host, weight_scale)
+                    secs.append(dr.last_seconds)
+                pred_s = float(np.mean(secs))
+                assert np.array_equal(out_pred.view(np.uint32), out_host.view(np.uint32)), "predict() != C ABI forward"
+                e2e = {"value": max(e_total, 1) / pred_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * m + 16 * n + 4 * n),
+                       "d2h_bytes_per_step": int(4 * n), "ms_per_step": pred_s * 1e3, "first_call_ms": first * 1e3,
+                       "what": "gnn::model::predict(in, out, reduction_graph) through the reference's C++ interface "
+                               "(host/gvc_dropin_capi.cpp), per step: adjacency read from the reduction_graph, staged "
+                               "through pinned memory and uploaded (ids + per-vertex ranges, weights), CSR compaction, "
+                               "checks and degree schedule on the device, H2D of x, 3 fused kernels, D2H of the scores "
+                               "into the host matrix; wall clock of predict()",
+                       "c_abi": c_abi, "csr_resident": resident}
+                dr.graph_destroy(dg)
+                dr.model_destroy(dm)
+        if e2e is None:
+            e2e = dict(c_abi, c_abi=None, csr_resident=resident,
+                       what=c_abi["what"] + " (predict() leg not run: graph too large for a host reduction_graph "
+                                            "in the bench's time, or the drop-in binding is not built)")
     else:
         # every rank takes its shard's CSR from pinned host buffers, uploads it (copies, checks, degree
         # schedule), copies x, runs the three stages with the two exchanges and reads its scores back
@@ -462,6 +549,31 @@ def run_ours(args):
                                 "h2d_bytes_per_step": int(4 * n) * world, "d2h_bytes_per_step": int(4 * n),
                                 "what": "the same without the per-step shard upload"}}
 
+    # ---- N > 1: the sharded scores against a 1-GPU forward of the same graph (outside any timed region)
+    parity = None
+    if world > 1:
+        torch.cuda.synchronize()
+        gathered = gdist.gather_scores(scores, bounds)
+        one = pkg.Context(local_rank)
+        one.model_upload(layers)
+        one.graph_adopt(g.row_ptr.to(torch.int32).contiguous(), g.col, g.weights, g.nw)
+        one.graph_set_tail(int(_perm[n - 1].item()) if n % 2 else None)
+        one_scores = torch.empty(g.n, device=dev)
+        one.forward_device(x_full, weight_scale, one_scores, mode)
+        one.sync()
+        torch.cuda.synchronize()
+        if mode == pkg.MODE_EXACT:
+            same = bool(torch.equal(gathered.view(torch.int32), one_scores.view(torch.int32)))
+        else:   # fast mode splits hub sums by shard-local chunk lists: equal within the fast tolerance
+            same = bool(((gathered - one_scores).abs() <= 1e-4 * one_scores.abs().clamp_min(1e-30)).all())
+        ok = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity = {"equal": bool(ok.item()), "compared": "bit for bit" if mode == pkg.MODE_EXACT else "within 1e-4 relative",
+                  "checksum_sharded": int(gathered.view(torch.int32).to(torch.int64).sum().item()),
+                  "checksum_1gpu": int(one_scores.view(torch.int32).to(torch.int64).sum().item())}
+        one.close()
+        del one_scores, gathered
+
     if rank == 0:
         peak, peak_src = load_peaks()
         b0, b1, b2 = algorithmic_bytes(n, m)
@@ -481,7 +593,11 @@ def run_ours(args):
                     "forward_frac": (b0 + b1 + b2) / (total_ms / args.steps * 1e-3) / 1e9 / peak}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_leg(layers)
+            if g_cpu is None:      # a workload too large for the CPU leg's budget: a scale-20 sample of the generator
+                gs = graphs.rmat_graph(20, 16, seed=42, device=dev)
+                g_cpu = {"n": gs.n, "eu": gs.eu.cpu().numpy().astype(np.uint32), "ev": gs.ev.cpu().numpy().astype(np.uint32),
+                         "w": gs.weights.cpu().numpy().view(np.uint32).copy(), "sample": True}
+            cpu = cpu_baseline_leg(layers, g_cpu)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -492,10 +608,17 @@ def run_ours(args):
                        "sharding": "single GPU" if world == 1 else f"{world} equal vertex ranges of the relabelled graph (vertices dealt to the shards by descending degree: equal counts, equal nnz), " + ("the stage kernels store every 16-float row into the h buffers of the ranks that own a neighbour of its vertex, over NVLink (CUDA IPC peer memory), a one-element NCCL all-reduce as barrier after stages 0 and 1" if pr else "NCCL all-gather of the 16-float rows of the non-isolated vertices after stages 0 and 1" + (f" [{pr_note}]" if pr_note else "")),
                        "graph_generation_s": round(gen_s, 2)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "phase_ms": phase_ms, "other_mode": other,
+            "roofline": roof, "cpu_baseline": cpu, "phase_ms": phase_ms, "other_mode": other, "parity_vs_1gpu": parity,
             "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
         }
         emit(line)
+    # ---- teardown in dependency order, then a normal interpreter exit (exit hooks must run) ----------
+    torch.cuda.synchronize()
+    if pr is not None:
+        h1 = h2 = None
+        pr.close()
+    del h1, h2, scores, flush, x_full, shard, rp32, g
+    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -544,9 +667,4 @@ def main():
 
 
 if __name__ == "__main__":
-    rc = main()
-    sys.stdout.flush()
-    sys.stderr.flush()
-    # skip interpreter teardown: torch would free tensors that were used on the library's stream
-    # after that stream is gone
-    os._exit(rc or 0)
+    sys.exit(main() or 0)

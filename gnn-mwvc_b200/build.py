@@ -67,6 +67,26 @@ def build_dropin(force: bool = False) -> Path | None:
     return out
 
 
+def build_dropin_capi(force: bool = False) -> Path | None:
+    """host/_build/libgvc_dropin.so: the drop-in host units behind a C binding of the reference's C++
+    interface (host/gvc_dropin_capi.cpp), for Python callers (gnn-mwvc_b200/dropin.py)."""
+    if not (REF / "include" / "gnn_inference.hpp").exists():
+        out = PKG / "host" / "_build" / "libgvc_dropin.so"
+        return out if out.exists() else None
+    out = PKG / "host" / "_build" / "libgvc_dropin.so"
+    srcs = [PKG / "host" / "gvc_dropin_capi.cpp", PKG / "host" / "gvc_gnn_inference.cpp", PKG / "host" / "gvc_matrix.cpp",
+            ROOT / "include" / "gvc.h", PKG / "host" / "gvc_host_ctx.hpp"]
+    if force or _stale(out, srcs + [PKG / "libgvc.so"]):
+        out.parent.mkdir(parents=True, exist_ok=True)
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O3", "-march=x86-64-v3", "-DNDEBUG", "-fPIC", "-shared",
+               "-I", str(REF / "include"), "-I", str(ROOT / "include"), "-I", str(PKG / "host"), "-o", str(out),
+               str(srcs[0]), str(srcs[1]), str(srcs[2]),
+               "-L", str(PKG), "-lgvc", "-pthread", "-Wl,--disable-new-dtags,-rpath,$ORIGIN/../.."]
+        subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build_libgvc(force=True, verbose=True))
     print(build_dropin(force=True))
+    print(build_dropin_capi(force=True))

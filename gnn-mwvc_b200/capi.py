@@ -30,6 +30,7 @@ SIGNATURES = {
     "gvc_ctx_destroy": (None, [C.c_void_p]),
     "gvc_model_upload": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p, _i32p, C.POINTER(_f32p), C.POINTER(_f32p)]),
     "gvc_model_is_fused": (C.c_int, [C.c_void_p]),
+    "gvc_model_weight_scales": (C.c_int, [C.c_void_p, C.c_int, _f32p]),
     "gvc_graph_upload": (C.c_int, [C.c_void_p, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
     "gvc_graph_upload_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
     "gvc_graph_staging": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(_u64p), C.POINTER(_u32p),
@@ -159,6 +160,11 @@ class Context:
     @property
     def fused(self) -> bool:
         return bool(self.lib.gvc_model_is_fused(self.h))
+
+    def weight_scales(self, scales):
+        """Per-graph-layer WEIGHT_SCALE (None / empty: every layer uses the forward call's scalar)."""
+        a = np.ascontiguousarray(scales if scales is not None else [], np.float32)
+        self._check(self.lib.gvc_model_weight_scales(self.h, a.size, _ptr(a, _f32p)))
 
     # -- graph ---------------------------------------------------------------
     def graph_upload(self, row_ptr, col, W, NW, n_global=None, v_begin=0, v_end=None):

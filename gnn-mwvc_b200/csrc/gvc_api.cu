@@ -111,6 +111,7 @@ struct gvc_ctx {
     std::vector<HostLayer> layers;
     bool fused = false;
     float *d_stage_params[3] = {nullptr, nullptr, nullptr};
+    std::vector<float> layer_scales;     // gvc_model_weight_scales: WEIGHT_SCALE of every graph layer (empty: the call's scalar)
 
     // graph shard
     bool have_graph = false;
@@ -215,7 +216,82 @@ __global__ void generic_graph_kernel(const uint32_t *__restrict__ row_ptr, const
     out[idx] = v;
 }
 
-// linear_layer::forward :20-25 in the operation order of oracle/gnn_oracle.c
+// ---- dot(), src/matrix.cpp:106-122: the cblas_sgemm call in OpenBLAS' operation order ------------
+// OpenBLAS 0.3.15 "Prescott" (8x4 SSE3 micro-kernel, no FMA), one thread, in row-major terms
+// (oracle/gnn_oracle.c holds the derivation): rows go 4 at a time, then 2, then 1; columns 8, 4, 2, 1;
+// the (row class, column class) pair fixes how the k sum of an element is split over accumulators; k is
+// cut into blocks of 128 (a rest of 129..255 is halved), every block's sum is added to C in turn.
+enum { kSumSeq = 0, kSumTwo = 1, kSumFour = 2, kSumEight = 3 };
+
+__device__ __forceinline__ int blas_row_class(uint64_t i, uint64_t m) {
+    const uint64_t m4 = m & ~3ull;
+    if (i < m4) return 0;
+    if ((m & 2) && i < m4 + 2) return 1;
+    return 2;
+}
+__device__ __forceinline__ int blas_col_class(uint64_t j, uint64_t n) {
+    uint64_t p = n & ~7ull;
+    if (j < p) return 0;
+    if (n & 4) { if (j < p + 4) return 1; p += 4; }
+    if (n & 2) { if (j < p + 2) return 2; p += 2; }
+    return 3;
+}
+__device__ __forceinline__ int blas_sum_scheme(int rc, int cc) {
+    // rows: 4 | 2 | 1 ; cols: 8 4 2 1
+    const int t = rc == 0 ? 0x0011 : rc == 1 ? 0x0111 : 0x1132;      // nibbles, column class 0 (8 cols) is the top one
+    return (t >> (4 * (3 - cc))) & 0xF;
+}
+
+// one k block [lo, hi) of one element: a[k * sa] * b[k * sb]
+__device__ __forceinline__ float blas_block_sum(const float *__restrict__ a, uint64_t sa, const float *__restrict__ b,
+                                                uint64_t sb, uint64_t lo, uint64_t hi, int scheme) {
+    const uint64_t K = hi - lo;
+    a += lo * sa; b += lo * sb;
+    uint64_t k = 0;
+    if (scheme == kSumSeq) {
+        float acc = 0.0f;
+        for (; k < K; ++k) acc = __fadd_rn(acc, __fmul_rn(a[k * sa], b[k * sb]));
+        return acc;
+    }
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f, c6 = 0.f, c7 = 0.f;
+    auto mac = [&](float &c, uint64_t kk) { c = __fadd_rn(c, __fmul_rn(a[kk * sa], b[kk * sb])); };
+    if (scheme == kSumTwo) {
+        const uint64_t body = K / 8 * 8;
+        for (; k < body; k += 2) { mac(c0, k); mac(c1, k + 1); }
+        for (; k < K; ++k) mac(c0, k);
+        return __fadd_rn(c0, c1);
+    }
+    if (scheme == kSumFour) {
+        const uint64_t body = K / 8 * 8;
+        for (; k < body; k += 4) { mac(c0, k); mac(c1, k + 1); mac(c2, k + 2); mac(c3, k + 3); }
+        for (; k < K; ++k) mac(c0, k);
+        return __fadd_rn(__fadd_rn(c0, c1), __fadd_rn(c2, c3));
+    }
+    const uint64_t body = K / 16 * 16;
+    for (; k < body; k += 8) {
+        mac(c0, k); mac(c1, k + 1); mac(c2, k + 2); mac(c3, k + 3);
+        mac(c4, k + 4); mac(c5, k + 5); mac(c6, k + 6); mac(c7, k + 7);
+    }
+    for (; k < K; ++k) mac(c0, k);
+    return __fadd_rn(__fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c4, c6)), __fadd_rn(__fadd_rn(c1, c3), __fadd_rn(c5, c7)));
+}
+
+// element (i, j) of op(A) op(B) + c_in over all k blocks; c_in = beta * C (0 for beta == 0)
+__device__ __forceinline__ float blas_dot_element(const float *__restrict__ a, uint64_t sa, const float *__restrict__ b,
+                                                  uint64_t sb, uint64_t k, int scheme, float c_in) {
+    float c = c_in;
+    uint64_t lo = 0;
+    while (lo < k) {
+        uint64_t len = k - lo;
+        if (len >= 256) len = 128;
+        else if (len > 128) len = (len / 2 + 7) / 8 * 8;
+        c = __fadd_rn(c, blas_block_sum(a, sa, b, sb, lo, lo + len, scheme));
+        lo += len;
+    }
+    return c;
+}
+
+// linear_layer::forward :20-25: dot(in, W, out) with beta = 0, then the row-wise bias add
 template <bool EXACT>
 __global__ void generic_linear_kernel(const float *__restrict__ in, int K, int Nout,
                                       const float *__restrict__ Wm, const float *__restrict__ bias,
@@ -231,28 +307,8 @@ __global__ void generic_linear_kernel(const float *__restrict__ in, int K, int N
         for (int k = 0; k < K; ++k) acc = fmaf(a[k], Wm[(size_t)k * Nout + j], acc);
         r = acc;
     } else {
-        const bool last_odd = (n & 1) && i == n - 1;
-        const int K8 = K / 8 * 8;
-        if (Nout == 1 && last_odd) {
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            int k = 0;
-            for (; k < K8; ++k) c[k & 3] = __fadd_rn(c[k & 3], __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
-            for (; k < K; ++k) c[0] = __fadd_rn(c[0], __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
-            r = __fadd_rn(__fadd_rn(c[0], c[1]), __fadd_rn(c[2], c[3]));
-        } else if (Nout == 1 || last_odd) {
-            float ev = 0.0f, od = 0.0f;
-            int k = 0;
-            for (; k < K8; k += 2) {
-                ev = __fadd_rn(ev, __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
-                od = __fadd_rn(od, __fmul_rn(a[k + 1], Wm[(size_t)(k + 1) * Nout + j]));
-            }
-            for (; k < K; ++k) ev = __fadd_rn(ev, __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
-            r = __fadd_rn(ev, od);
-        } else {
-            float acc = 0.0f;
-            for (int k = 0; k < K; ++k) acc = __fadd_rn(acc, __fmul_rn(a[k], Wm[(size_t)k * Nout + j]));
-            r = acc;
-        }
+        r = blas_dot_element(a, 1, Wm + j, (uint64_t)Nout, (uint64_t)K,
+                             blas_sum_scheme(blas_row_class(i, n), blas_col_class((uint64_t)j, (uint64_t)Nout)), 0.0f);
     }
     out[idx] = __fadd_rn(r, bias[j]);
 }
@@ -268,21 +324,19 @@ __global__ void generic_sigmoid_kernel(const float *__restrict__ in, float *__re
     if (idx < count) out[idx] = sigmoid_ref<EXACT>(in[idx]);
 }
 
-// dot(), src/matrix.cpp:106-122: C = op(A) op(B) + beta C, one thread per element of C
+// dot(), src/matrix.cpp:106-122: C = op(A) op(B) + beta C, one thread per element of C, in the
+// reference's (OpenBLAS') summation order for every shape, transpose and beta
 __global__ void generic_sgemm_kernel(int ta, int tb, uint64_t m, uint64_t n, uint64_t k,
                                      const float *__restrict__ A, uint64_t lda, const float *__restrict__ B,
                                      uint64_t ldb, float beta, float *__restrict__ Cm, uint64_t ldc) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= m * n) return;
     const uint64_t i = idx / n, j = idx % n;
-    float acc = 0.0f;
-    for (uint64_t p = 0; p < k; ++p) {
-        const float a = ta ? A[p * lda + i] : A[i * lda + p];
-        const float b = tb ? B[j * ldb + p] : B[p * ldb + j];
-        acc = __fadd_rn(acc, __fmul_rn(a, b));
-    }
+    const float *a = ta ? A + i : A + i * lda;
+    const float *b = tb ? B + j * ldb : B + j;
     float *c = Cm + i * ldc + j;
-    *c = beta == 0.0f ? acc : __fadd_rn(acc, __fmul_rn(beta, *c));
+    const float c_in = beta == 0.0f ? 0.0f : __fmul_rn(beta, *c);
+    *c = blas_dot_element(a, ta ? lda : 1, b, tb ? 1 : ldb, k, blas_sum_scheme(blas_row_class(i, m), blas_col_class(j, n)), c_in);
 }
 
 inline unsigned blocks_for(uint64_t work, int threads) { return (unsigned)((work + threads - 1) / threads); }
@@ -313,16 +367,33 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     HubSplit hub{c->d_hub_chunk[hk].p, c->d_hub_info[hk].p, c->d_hub_partial[hk].p,
                  c->d_sync.p + kSyncCounters + sc.n_feat_tiles};
     GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (kSyncCounters + (size_t)sc.n_feat_tiles + (exact ? 0 : n_split)) * sizeof(uint32_t), c->stream));
+    // Cooperative launch: warps of this persistent kernel wait for feature vectors that other CTAs
+    // produce, so every CTA of the grid must be resident at once.  The grid is sized for that (above);
+    // the launch attribute makes the driver guarantee it even when the stream shares the GPU with other
+    // work (a framework stream, MPS, concurrent kernels) instead of relying on dispatch order.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kCtaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute coop{};
+    coop.id = cudaLaunchAttributeCooperative;
+    coop.val.cooperative = 1;
+    cfg.attrs = &coop;
+    cfg.numAttrs = 1;
+    const uint32_t *a_rp = c->row_ptr, *a_col = c->col, *a_w = c->Wv, *a_nw = c->NWv, *a_order = c->d_order.p;
+    const uint4 *a_vrec = c->d_vrec.p;
+    float *a_feat = c->d_feat.p;
+    uint32_t *a_sync = c->d_sync.p;
+    const float *a_params = c->d_stage_params[STAGE];
+    const uint32_t a_vb = c->v_begin;
     if (mode == GVC_MODE_EXACT) {
-        stage_kernel<STAGE, true><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, hub, peers, c->d_feat.p, c->d_sync.p, d_in, d_out,
-            c->d_stage_params[STAGE], c->v_begin, scale);
+        GVC_CUDA(cudaLaunchKernelEx(&cfg, stage_kernel<STAGE, true>, a_rp, a_col, a_w, a_nw, a_order, a_vrec, sc_launch, hub, peers,
+                                    a_feat, a_sync, d_in, d_out, a_params, a_vb, scale));
     } else {
-        stage_kernel<STAGE, false><<<grid, kCtaThreads, smem, c->stream>>>(
-            c->row_ptr, c->col, c->Wv, c->NWv, c->d_order.p, c->d_vrec.p, sc_launch, hub, peers, c->d_feat.p, c->d_sync.p, d_in, d_out,
-            c->d_stage_params[STAGE], c->v_begin, scale);
+        GVC_CUDA(cudaLaunchKernelEx(&cfg, stage_kernel<STAGE, false>, a_rp, a_col, a_w, a_nw, a_order, a_vrec, sc_launch, hub, peers,
+                                    a_feat, a_sync, d_in, d_out, a_params, a_vb, scale));
     }
-    GVC_CUDA(cudaGetLastError());
     c->launches++;
     // OpenBLAS' 1-row remainder kernel: last vertex of an odd-sized graph (exact mode only)
     const bool default_tail = (c->n_global & 1u) && c->v_end == c->n_global;
@@ -448,7 +519,9 @@ int build_schedule(gvc_ctx *c) {
     GVC_CUDA(cudaStreamSynchronize(c->stream));   // `start` and `n_chunks` live on this stack frame
     sc.n_chunks16 = (uint32_t)std::min<uint64_t>(n_chunks[0], c->nnz / kChunk16 + n_ring);
     sc.n_chunks1 = (uint32_t)std::min<uint64_t>(n_chunks[1], c->nnz / kChunk1 + n_giant1);
-    return build_peer_mask(c);
+    // (the per-vertex peer lists read the adjacency itself: the callers build them once it has landed)
+    c->have_peer_mask = false;
+    return 0;
 }
 
 template <int STAGE>
@@ -500,6 +573,7 @@ int forward_generic(gvc_ctx *c, const float *d_x, float scale, float *d_scores, 
     int which = 0;
     w = 1;
     const int T = 256;
+    size_t gi = 0;                       // index among the graph layers
     for (size_t li = 0; li < c->layers.size(); ++li) {
         auto &l = c->layers[li];
         const bool last = li + 1 == c->layers.size();
@@ -514,10 +588,13 @@ int forward_generic(gvc_ctx *c, const float *d_x, float scale, float *d_scores, 
             else
                 generic_linear_kernel<false><<<blocks_for((uint64_t)n * wo, T), T, 0, c->stream>>>(cur, l.rows, l.cols, l.dW, l.db, dst, n);
             break;
-        case GVC_GRAPH:
+        case GVC_GRAPH: {
             wo = 2 * w + 3;
-            generic_graph_kernel<<<blocks_for((uint64_t)n * wo, T), T, 0, c->stream>>>(c->row_ptr, c->col, c->Wv, c->NWv, cur, w, dst, n, 0, scale);
+            const float ls = gi < c->layer_scales.size() ? c->layer_scales[gi] : scale;   // this layer's own WEIGHT_SCALE
+            ++gi;
+            generic_graph_kernel<<<blocks_for((uint64_t)n * wo, T), T, 0, c->stream>>>(c->row_ptr, c->col, c->Wv, c->NWv, cur, w, dst, n, 0, ls);
             break;
+        }
         case GVC_RELU:
             generic_relu_kernel<<<blocks_for((uint64_t)n * w, T), T, 0, c->stream>>>(cur, dst, (uint64_t)n * w);
             break;
@@ -622,35 +699,63 @@ int gvc_model_upload(gvc_ctx *c, int n_layers, const int *kinds, const int *rows
     int rc;
     if ((rc = check_ctx(c))) return rc;
     if (n_layers <= 0 || !kinds) return fail(GVC_ERR_ARG, "empty model");   // assert(!layers.empty()), :68
-    if ((rc = use_device(c))) return rc;
-    for (auto &l : c->layers) { if (l.dW) cudaFree(l.dW); if (l.db) cudaFree(l.db); }
-    c->layers.clear();
-    for (auto &p : c->d_stage_params) { if (p) cudaFree(p); p = nullptr; }
-    c->layers.resize(n_layers);
+    // validate everything before the context is touched: a rejected model leaves the old one in place
     for (int i = 0; i < n_layers; ++i) {
-        HostLayer &l = c->layers[i];
-        l.kind = kinds[i];
-        if (l.kind < GVC_LINEAR || l.kind > GVC_SIGMOID) return fail(GVC_ERR_ARG, "layer %d: unknown kind %d", i, l.kind);
-        if (l.kind != GVC_LINEAR) continue;
+        if (kinds[i] < GVC_LINEAR || kinds[i] > GVC_SIGMOID) return fail(GVC_ERR_ARG, "layer %d: unknown kind %d", i, kinds[i]);
+        if (kinds[i] != GVC_LINEAR) continue;
         if (!rows || !cols || !W || !bias || !W[i] || !bias[i] || rows[i] <= 0 || cols[i] <= 0)
             return fail(GVC_ERR_ARG, "layer %d: linear layer needs rows, cols, W and bias", i);
-        l.rows = rows[i]; l.cols = cols[i];
-        l.W.assign(W[i], W[i] + (size_t)l.rows * l.cols);
-        l.b.assign(bias[i], bias[i] + l.cols);
-        GVC_CUDA(cudaMalloc(&l.dW, l.W.size() * sizeof(float)));
-        GVC_CUDA(cudaMalloc(&l.db, l.b.size() * sizeof(float)));
-        GVC_CUDA(cudaMemcpyAsync(l.dW, l.W.data(), l.W.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-        GVC_CUDA(cudaMemcpyAsync(l.db, l.b.data(), l.b.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
-    c->fused = detect_fused(c->layers);
-    if (c->fused) {
-        for (int s = 0; s < 3; ++s) {
-            std::vector<float> p = pack_stage(c->layers, s);
-            GVC_CUDA(cudaMalloc(&c->d_stage_params[s], p.size() * sizeof(float)));
-            GVC_CUDA(cudaMemcpy(c->d_stage_params[s], p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if ((rc = use_device(c))) return rc;
+    GVC_CUDA(cudaStreamSynchronize(c->stream));      // no forward may still read the old parameters
+    // From here on a failure (CUDA allocation or copy) leaves the context WITHOUT a model -- never
+    // with a half-built one that the stage kernels could be launched on.
+    auto drop_model = [c] {
+        for (auto &l : c->layers) { if (l.dW) cudaFree(l.dW); if (l.db) cudaFree(l.db); }
+        c->layers.clear();
+        for (auto &p : c->d_stage_params) { if (p) cudaFree(p); p = nullptr; }
+        c->fused = false;
+        c->layer_scales.clear();
+    };
+    drop_model();
+    auto upload = [&]() -> int {
+        c->layers.resize(n_layers);
+        for (int i = 0; i < n_layers; ++i) {
+            HostLayer &l = c->layers[i];
+            l.kind = kinds[i];
+            if (l.kind != GVC_LINEAR) continue;
+            l.rows = rows[i]; l.cols = cols[i];
+            l.W.assign(W[i], W[i] + (size_t)l.rows * l.cols);
+            l.b.assign(bias[i], bias[i] + l.cols);
+            GVC_CUDA(cudaMalloc(&l.dW, l.W.size() * sizeof(float)));
+            GVC_CUDA(cudaMalloc(&l.db, l.b.size() * sizeof(float)));
+            GVC_CUDA(cudaMemcpyAsync(l.dW, l.W.data(), l.W.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            GVC_CUDA(cudaMemcpyAsync(l.db, l.b.data(), l.b.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         }
-    }
-    GVC_CUDA(cudaStreamSynchronize(c->stream));
+        if (detect_fused(c->layers)) {
+            for (int s = 0; s < 3; ++s) {
+                std::vector<float> p = pack_stage(c->layers, s);
+                GVC_CUDA(cudaMalloc(&c->d_stage_params[s], p.size() * sizeof(float)));
+                GVC_CUDA(cudaMemcpy(c->d_stage_params[s], p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+            }
+        }
+        GVC_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    if ((rc = upload())) { drop_model(); return rc; }
+    c->fused = detect_fused(c->layers);              // only a completely uploaded model is ever "fused"
+    return 0;
+}
+
+int gvc_model_weight_scales(gvc_ctx *c, int n_graph_layers, const float *scales) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (n_graph_layers == 0) { c->layer_scales.clear(); return 0; }
+    int have = 0;
+    for (auto &l : c->layers) have += l.kind == GVC_GRAPH;
+    if (n_graph_layers != have) return fail(GVC_ERR_ARG, "%d scales for a model with %d graph layers", n_graph_layers, have);
+    if (!scales) return fail(GVC_ERR_ARG, "null scales");
+    c->layer_scales.assign(scales, scales + n_graph_layers);
     return 0;
 }
 
@@ -720,6 +825,13 @@ int gvc_graph_upload_shard(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
     }
     tr.tick("upload: schedule");
     GVC_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));           // forwards start after the adjacency landed
+    // the peer lists are read off the adjacency: only now is it complete on this stream (building them
+    // inside the schedule raced with the copy when gvc_peer_owners had been called before the upload)
+    if ((rc = build_peer_mask(c))) {
+        cudaStreamSynchronize(c->copy_stream);
+        c->have_graph = false;
+        return rc;
+    }
     GVC_CUDA(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));                        // also: the caller's buffers are free again
     if (flag) {
@@ -775,7 +887,8 @@ int gvc_graph_adopt_device(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
         GVC_CUDA(cudaMemcpyAsync(c->own_col.p, d_col, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, c->stream));
         col = c->own_col.p;
     }
-    return set_graph_views(c, n_global, v_begin, v_end, d_row_ptr, col, d_W, d_NW, nnz);
+    if ((rc = set_graph_views(c, n_global, v_begin, v_end, d_row_ptr, col, d_W, d_NW, nnz))) return rc;
+    return build_peer_mask(c);          // same stream as the copy above: ordered
 }
 
 int gvc_graph_set_tail(gvc_ctx *c, int has_tail, uint32_t local_index) {
@@ -908,9 +1021,13 @@ int gvc_forward_device(gvc_ctx *c, const float *d_x, float scale, float *d_score
     if (!d_x || !d_scores) return fail(GVC_ERR_ARG, "null buffer");
     if ((rc = use_device(c))) return rc;
     if (!c->fused) return forward_generic(c, d_x, scale, d_scores, mode);
-    if ((rc = launch_stage<0>(c, d_x, c->d_h1.p, scale, mode))) return rc;
-    if ((rc = launch_stage<1>(c, c->d_h1.p, c->d_h2.p, scale, mode))) return rc;
-    return launch_stage<2>(c, c->d_h2.p, d_scores, scale, mode);
+    // graph_layer::WEIGHT_SCALE is per layer (src/gnn_inference.cpp:38-40): stage s divides by its own
+    const float s0 = c->layer_scales.size() == 3 ? c->layer_scales[0] : scale;
+    const float s1 = c->layer_scales.size() == 3 ? c->layer_scales[1] : scale;
+    const float s2 = c->layer_scales.size() == 3 ? c->layer_scales[2] : scale;
+    if ((rc = launch_stage<0>(c, d_x, c->d_h1.p, s0, mode))) return rc;
+    if ((rc = launch_stage<1>(c, c->d_h1.p, c->d_h2.p, s1, mode))) return rc;
+    return launch_stage<2>(c, c->d_h2.p, d_scores, s2, mode);
 }
 
 int gvc_forward(gvc_ctx *c, const float *x, float scale, float *scores, int mode) {

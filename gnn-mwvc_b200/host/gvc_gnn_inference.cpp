@@ -255,9 +255,19 @@ void model::predict(const matrix &in, matrix &out, const reduction_graph<Tn, Tw>
     gvc_ctx *ctx = gvc_host::context();
     upload_model_if_stale(ctx, this, layers);
 
+    // every graph layer divides by its OWN WEIGHT_SCALE (src/gnn_inference.cpp:38-40); after
+    // set_weight_scale they are all equal and one scalar does, a model built with add_layer may differ
     float scale = 120.0f;   // graph_layer::WEIGHT_SCALE default, include/gnn_inference.hpp:25
+    std::vector<float> scales;
     for (auto &c : layers)
-        if (auto *gl = std::get_if<graph_layer>(&c)) { scale = gl->WEIGHT_SCALE; break; }
+        if (auto *gl = std::get_if<graph_layer>(&c)) scales.push_back(gl->WEIGHT_SCALE);
+    if (!scales.empty()) scale = scales[0];
+    const bool uniform = std::all_of(scales.begin(), scales.end(), [&](float v) { return v == scale; });
+    {
+        const int rc0 = uniform ? gvc_model_weight_scales(ctx, 0, nullptr)
+                                : gvc_model_weight_scales(ctx, (int)scales.size(), scales.data());
+        if (rc0 != 0) gvc_host::die("gvc_model_weight_scales", rc0);
+    }
 
     predict_profile &pf = profile();
     const double t0 = now_s();

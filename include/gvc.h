@@ -76,6 +76,14 @@ int gvc_model_upload(gvc_ctx *ctx, int n_layers, const int *kinds, const int *ro
 /* 1 if the uploaded model runs on the fused three-kernel path, else 0. */
 int gvc_model_is_fused(const gvc_ctx *ctx);
 
+/* graph_layer::WEIGHT_SCALE is a member of EVERY graph layer (include/gnn_inference.hpp:25, read at
+ * src/gnn_inference.cpp:39-40); model::set_weight_scale (:83-90) makes them equal, but a model built
+ * with add_layer may carry different ones.  scales[i] is the scale of the i-th graph layer of the
+ * uploaded model (n_graph_layers must match it).  While set, these take precedence over the
+ * weight_scale argument of the forward calls; n_graph_layers = 0 forgets them (and so does a model
+ * upload). */
+int gvc_model_weight_scales(gvc_ctx *ctx, int n_graph_layers, const float *scales);
+
 /* ---- graph: what predict reads through reduction_graph's accessors ---------
  * size() include/reduction_graph.hpp:141, begin(u)/end(u) :692-704, D :144,
  * W :147-151, NW :153-158, as used at src/gnn_inference.cpp:32-40.

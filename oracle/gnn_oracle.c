@@ -126,6 +126,14 @@ void gvo_model_set_weight_scale(gvo_model *m, float ws) {
         if (m->layers[i].kind == GVO_GRAPH) m->layers[i].weight_scale = ws;
 }
 
+/* graph_layer::WEIGHT_SCALE is a member of every graph layer (gnn_inference.hpp:25): a model built with
+ * add_layer may carry a different one per layer.  which = 0, 1, ... counts graph layers. */
+int gvo_model_set_graph_layer_scale(gvo_model *m, int which, float ws) {
+    for (int i = 0; i < m->n_layers; i++)
+        if (m->layers[i].kind == GVO_GRAPH && which-- == 0) { m->layers[i].weight_scale = ws; return 0; }
+    return -1;
+}
+
 float gvo_model_weight_scale(const gvo_model *m) {
     for (int i = 0; i < m->n_layers; i++)
         if (m->layers[i].kind == GVO_GRAPH) return m->layers[i].weight_scale;
@@ -154,69 +162,105 @@ void gvo_graph_forward(uint32_t n, const uint64_t *row_ptr, const uint32_t *col,
     }
 }
 
-/* Dot product in the order of OpenBLAS' remainder micro-kernels: k below
- * floor(K/8)*8 alternates between two accumulators (even k, odd k), the K%8
- * tail goes to the even one, result = even + odd. */
-static float dot_two_acc(const float *a, const float *Wm, int K, int Nout, int j) {
-    float ev = 0.0f, od = 0.0f;
-    int K8 = K / 8 * 8, k = 0;
-    for (; k < K8; k += 2) {
-        ev = ev + a[k] * Wm[(size_t)k * Nout + j];
-        od = od + a[k + 1] * Wm[(size_t)(k + 1) * Nout + j];
-    }
-    for (; k < K; k++) ev = ev + a[k] * Wm[(size_t)k * Nout + j];
-    return ev + od;
-}
-
-/* The 1-row x 1-column remainder kernel (last row of an odd n, Nout == 1): four
- * accumulators by k%4 below floor(K/8)*8, tail to the first, (a0+a1)+(a2+a3). */
-static float dot_four_acc(const float *a, const float *Wm, int K, int Nout, int j) {
-    float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    int K8 = K / 8 * 8, k = 0;
-    for (; k < K8; k++) c[k & 3] = c[k & 3] + a[k] * Wm[(size_t)k * Nout + j];
-    for (; k < K; k++) c[0] = c[0] + a[k] * Wm[(size_t)k * Nout + j];
-    return (c[0] + c[1]) + (c[2] + c[3]);
-}
-
-/* linear_layer::forward, gnn_inference.cpp:20-25 -> dot -> cblas_sgemm
- * (matrix.cpp:106-122), alpha=1, beta=0, then the row-wise bias add (:22-24).
+/* ---- dot(), matrix.cpp:106-122: cblas_sgemm, alpha = 1 -------------------------------------
  *
- * The arithmetic lives in OpenBLAS (un-vendored; the reference pins no version).
- * What is restated is the operation order of OpenBLAS 0.3.15, kernel "Prescott"
- * (sgemm 8x4 SSE3 micro-kernel), run with ONE thread, for the shapes of this
- * model (row-major C[n x Nout] = A[n x K] * W[K x Nout], K <= 35, Nout in
- * {1,16,32}); established by experiment against oracle/_ref and re-checked by
- * tests/test_oracle_vs_ref.py:
- *   - every output has its own accumulator chain, product and sum rounded
- *     separately (SSE3: no FMA);
- *   - rows (vertices) are taken 4 at a time, then 2, then 1.  The 4- and 2-row
- *     kernels walk k = 0..K-1 with a single accumulator;
- *   - the 1-row kernel (only the LAST row, only when n is odd) and the
- *     1-output-column kernel (Nout == 1, every row) use dot_two_acc above;
- *     where both apply (last row of an odd n, Nout == 1) it is dot_four_acc.
- * With several OpenBLAS threads the row range is cut into per-thread slices and
- * each slice has its own 2-/1-row tail, so a handful of rows per slice move by
- * an ulp; parity is therefore pinned at OPENBLAS_NUM_THREADS=1. */
+ * The arithmetic lives in OpenBLAS (un-vendored; the reference pins no version).  What is
+ * restated is the operation order of OpenBLAS 0.3.15, kernel set "Prescott" (sgemm 8x4 SSE3
+ * micro-kernel: no FMA, product and sum rounded separately), run with ONE thread; established by
+ * experiment against oracle/_ref (probes over every block class, transposes, K up to 2500) and
+ * re-checked by tests/test_oracle_vs_ref.py.  In row-major terms, C[m x n] = op(A) op(B):
+ *
+ *   rows are taken 4 at a time, then 2 (if m & 2), then 1 (if m & 1);
+ *   columns 8 at a time, then 4 (if n & 4), 2 (if n & 2), 1 (if n & 1);
+ *   the micro-kernel of a (row class, column class) pair fixes how the k sum of each element is
+ *   split over accumulators (transposes only change the packing, not the sums):
+ *
+ *                      8 cols   4 cols   2 cols   1 col
+ *        4 rows        SEQ      SEQ      TWO      TWO
+ *        2 rows        SEQ      TWO      TWO      TWO
+ *        1 row         TWO      TWO      EIGHT    FOUR
+ *
+ *     SEQ    one accumulator, k ascending
+ *     TWO    even / odd k below floor(K/8)*8, tail to the even one, even + odd
+ *     FOUR   k mod 4 below floor(K/8)*8, tail to the first, (a0+a1)+(a2+a3)
+ *     EIGHT  k mod 8 below floor(K/16)*16, tail to the first, ((a0+a2)+(a4+a6))+((a1+a3)+(a5+a7))
+ *
+ *   k is cut into blocks (GEMM_Q = 128: a remainder of >= 256 takes 128, one of 129..255 is halved
+ *   and rounded up to a multiple of 8, the rest goes in one piece); every block is one kernel call
+ *   with the sums above over its slice, added to C in turn; C is first scaled by beta (set to zero
+ *   for beta == 0).
+ * With several OpenBLAS threads the rows are cut into per-thread slices, each with its own 2-/1-row
+ * tail, so a handful of rows per slice move by an ulp; parity is pinned at OPENBLAS_NUM_THREADS=1. */
+enum { SUM_SEQ = 0, SUM_TWO = 1, SUM_FOUR = 2, SUM_EIGHT = 3 };
+
+static int row_class(size_t i, size_t m) {
+    size_t m4 = m & ~(size_t)3;
+    if (i < m4) return 0;
+    if ((m & 2) && i < m4 + 2) return 1;
+    return 2;
+}
+
+static int col_class(size_t j, size_t n) {
+    size_t p = n & ~(size_t)7;
+    if (j < p) return 0;
+    if (n & 4) { if (j < p + 4) return 1; p += 4; }
+    if (n & 2) { if (j < p + 2) return 2; p += 2; }
+    return 3;
+}
+
+static const int sum_scheme[3][4] = {{SUM_SEQ, SUM_SEQ, SUM_TWO, SUM_TWO},
+                                     {SUM_SEQ, SUM_TWO, SUM_TWO, SUM_TWO},
+                                     {SUM_TWO, SUM_TWO, SUM_EIGHT, SUM_FOUR}};
+
+/* one k block [lo, hi) of one element: a[k * sa], b[k * sb] */
+static float block_sum(const float *a, size_t sa, const float *b, size_t sb, size_t lo, size_t hi, int scheme) {
+    const size_t K = hi - lo;
+    a += lo * sa; b += lo * sb;
+    size_t k = 0;
+    if (scheme == SUM_SEQ) {
+        float acc = 0.0f;
+        for (; k < K; k++) acc = acc + a[k * sa] * b[k * sb];
+        return acc;
+    }
+    float c[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    const size_t w = scheme == SUM_TWO ? 2 : scheme == SUM_FOUR ? 4 : 8;
+    const size_t body = scheme == SUM_EIGHT ? K / 16 * 16 : K / 8 * 8;
+    for (; k < body; k++) c[k % w] = c[k % w] + a[k * sa] * b[k * sb];
+    for (; k < K; k++) c[0] = c[0] + a[k * sa] * b[k * sb];
+    if (scheme == SUM_TWO) return c[0] + c[1];
+    if (scheme == SUM_FOUR) return (c[0] + c[1]) + (c[2] + c[3]);
+    return ((c[0] + c[2]) + (c[4] + c[6])) + ((c[1] + c[3]) + (c[5] + c[7]));
+}
+
+/* dot(A, B, C, at, bt, beta), matrix.cpp:106-122.  A is stored k x m when at, else m x k; B n x k
+ * when bt, else k x n; C m x n; all row-major and dense. */
+void gvo_dot(int at, int bt, size_t m, size_t n, size_t k, const float *A, const float *B, float beta, float *C) {
+    const size_t sa = at ? m : 1, sb = bt ? 1 : n;
+    for (size_t i = 0; i < m; i++)
+        for (size_t j = 0; j < n; j++) {
+            const float *a = at ? A + i : A + i * k;
+            const float *b = bt ? B + j * k : B + j;
+            const int scheme = sum_scheme[row_class(i, m)][col_class(j, n)];
+            float c = beta == 0.0f ? 0.0f : beta * C[i * n + j];
+            size_t lo = 0;
+            while (lo < k) {
+                size_t len = k - lo;
+                if (len >= 256) len = 128;
+                else if (len > 128) len = (len / 2 + 7) / 8 * 8;
+                c = c + block_sum(a, sa, b, sb, lo, lo + len, scheme);
+                lo += len;
+            }
+            C[i * n + j] = c;
+        }
+}
+
+/* linear_layer::forward, gnn_inference.cpp:20-25: dot(in, W, out) with beta = 0, then the
+ * row-wise bias add (:22-24). */
 void gvo_linear_forward(size_t n, int K, int Nout, const float *in,
                         const float *Wm, const float *bias, float *out) {
-    for (size_t i = 0; i < n; i++) {
-        const float *a = in + i * (size_t)K;
-        float *o = out + i * (size_t)Nout;
-        int last_odd = (n & 1) && i == n - 1;
-        int two_acc = (Nout == 1) || last_odd;
-        for (int j = 0; j < Nout; j++) {
-            float acc;
-            if (Nout == 1 && last_odd) {
-                acc = dot_four_acc(a, Wm, K, Nout, j);
-            } else if (two_acc) {
-                acc = dot_two_acc(a, Wm, K, Nout, j);
-            } else {
-                acc = 0.0f;
-                for (int k = 0; k < K; k++) acc = acc + a[k] * Wm[(size_t)k * Nout + j];
-            }
-            o[j] = acc + bias[j];
-        }
-    }
+    gvo_dot(0, 0, n, (size_t)Nout, (size_t)K, in, Wm, 0.0f, out);
+    for (size_t i = 0; i < n; i++)
+        for (int j = 0; j < Nout; j++) out[i * (size_t)Nout + j] = out[i * (size_t)Nout + j] + bias[j];
 }
 
 /* ReLU::forward, gnn_inference.cpp:44-47: std::max(x, 0.0f) == (x < 0) ? 0 : x */

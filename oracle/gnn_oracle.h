@@ -42,6 +42,8 @@ int gvo_model_layer(const gvo_model *m, int i, int *rows, int *cols,
 /* set_weight_scale, gnn_inference.cpp:83-90 */
 void gvo_model_set_weight_scale(gvo_model *m, float ws);
 float gvo_model_weight_scale(const gvo_model *m);
+/* WEIGHT_SCALE of the which-th graph layer alone (a model built with add_layer may mix them). */
+int gvo_model_set_graph_layer_scale(gvo_model *m, int which, float ws);
 
 /* graph_layer::forward, gnn_inference.cpp:27-42, on a CSR view of the graph
  * (row_ptr[n+1], col = neighbour ids in the order g.begin(u)..g.end(u) yields
@@ -55,6 +57,11 @@ void gvo_graph_forward(uint32_t n, const uint64_t *row_ptr, const uint32_t *col,
  * OpenBLAS 0.3.15 "Prescott" for these shapes) + bias. */
 void gvo_linear_forward(size_t n, int K, int Nout, const float *in,
                         const float *Wm, const float *bias, float *out);
+
+/* dot(), matrix.cpp:106-122 (cblas_sgemm with alpha = 1): C[m x n] = op(A) op(B) + beta C in the
+ * operation order of OpenBLAS 0.3.15 "Prescott", one thread, for ANY shape (block classes, k
+ * blocking; see gnn_oracle.c).  A stored k x m when at, B stored n x k when bt; row-major, dense. */
+void gvo_dot(int at, int bt, size_t m, size_t n, size_t k, const float *A, const float *B, float beta, float *C);
 
 /* ReLU::forward :44-47 and sigmoid::forward :49-52 (elementwise, count floats) */
 void gvo_relu_forward(size_t count, const float *in, float *out);

@@ -83,6 +83,8 @@ class Oracle:
         L.gvo_predict.argtypes = [C.c_void_p, C.c_uint32, _u64p, _u32p, _u32p, _u32p, _f32p,
                                   C.c_int, _f32p, C.POINTER(C.c_int)]
         L.gvo_model_out_width.argtypes = [C.c_void_p, C.c_int]
+        L.gvo_dot.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, _f32p, _f32p, C.c_float, _f32p]
+        L.gvo_model_set_graph_layer_scale.argtypes = [C.c_void_p, C.c_int, C.c_float]
         self.L = L
 
     # -- model ---------------------------------------------------------------
@@ -145,6 +147,19 @@ class Oracle:
         self.L.gvo_sigmoid_forward(x.size, _p(x, _f32p), _p(out, _f32p))
         return out
 
+    def dot(self, A, B, C0=None, at=False, bt=False, beta=0.0):
+        """dot() of matrix.cpp:106-122 in the reference's operation order (A, B as stored)."""
+        A = np.ascontiguousarray(A, np.float32)
+        B = np.ascontiguousarray(B, np.float32)
+        m, k = (A.shape[1], A.shape[0]) if at else A.shape
+        n = B.shape[0] if bt else B.shape[1]
+        out = np.zeros((m, n), np.float32) if C0 is None else np.ascontiguousarray(C0, np.float32).copy()
+        self.L.gvo_dot(int(at), int(bt), m, n, k, _p(A, _f32p), _p(B, _f32p), float(beta), _p(out, _f32p))
+        return out
+
+    def set_graph_layer_scale(self, h, which: int, scale: float):
+        assert self.L.gvo_model_set_graph_layer_scale(h, which, float(scale)) == 0
+
     def predict(self, h, row_ptr, col, W, NW, x, scale=None):
         if scale is not None:
             self.L.gvo_model_set_weight_scale(h, float(scale))
@@ -176,12 +191,19 @@ def build_dropin_harness() -> Path | None:
 class Reference:
     """The unmodified reference (OpenBLAS kernel pinned to Prescott)."""
 
-    def __init__(self, threads: int | None = None, so: Path | None = None):
+    def __init__(self, threads: int | None = None, so: Path | None = None, coretype: str | None = "Prescott"):
+        """coretype: the OpenBLAS kernel set.  "Prescott" (default) is the one the oracle restates and
+        the golden vectors were made with -- every CHECKER use keeps it.  None leaves the choice to
+        OpenBLAS' own CPU detection (the TIMED reference arm of bench.py: the kernel a stock build
+        would run on this host).  Fixed at the first load of libopenblas in a process."""
         REF_SO = so or globals()["REF_SO"]
         if not REF_SO.exists():
             raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
         # must be set before libopenblas' constructor runs
-        os.environ.setdefault("OPENBLAS_CORETYPE", "Prescott")
+        if coretype is None:
+            os.environ.pop("OPENBLAS_CORETYPE", None)
+        else:
+            os.environ.setdefault("OPENBLAS_CORETYPE", coretype)
         if threads:
             os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
         L = C.CDLL(str(REF_SO))
@@ -190,6 +212,9 @@ class Reference:
         L.ref_model_create.restype = C.c_void_p
         L.ref_model_create.argtypes = [C.c_char_p]
         L.ref_model_destroy.argtypes = [C.c_void_p]
+        L.ref_model_build.restype = C.c_void_p
+        L.ref_model_build.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(_f32p), C.POINTER(_f32p), _f32p]
         L.ref_model_set_weight_scale.argtypes = [C.c_void_p, C.c_float]
         L.ref_model_text.restype = C.c_size_t
         L.ref_model_text.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
@@ -201,6 +226,16 @@ class Reference:
         L.ref_relu.argtypes = [C.c_size_t, _f32p, _f32p]
         L.ref_sigmoid.argtypes = [C.c_size_t, _f32p, _f32p]
         L.ref_linear_init.argtypes = [C.c_int, C.c_int, C.c_size_t, _f32p]
+        L.ref_dot.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, _f32p, _f32p, C.c_float, _f32p]
+        L.ref_graph_create.restype = C.c_void_p
+        L.ref_graph_create.argtypes = [C.c_uint32, C.c_uint64, _u32p, _u32p, _u32p]
+        L.ref_graph_destroy.argtypes = [C.c_void_p]
+        L.ref_graph_size.restype = C.c_uint32
+        L.ref_graph_size.argtypes = [C.c_void_p]
+        L.ref_graph_mutate.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]
+        L.ref_graph_csr.restype = C.c_uint64
+        L.ref_graph_csr.argtypes = [C.c_void_p, _u64p, _u32p, _u32p, _u32p, C.POINTER(C.c_uint8)]
+        L.ref_predict_on.argtypes = [C.c_void_p, C.c_void_p, _f32p, _f32p, C.c_int, C.POINTER(C.c_double)]
         self.L = L
         if threads:
             L.ref_blas_threads(threads)
@@ -210,6 +245,35 @@ class Reference:
 
     def model(self, text: str):
         return self.L.ref_model_create(text.encode())
+
+    def model_build(self, layers, scales=None):
+        """A model assembled with add_layer: layers = [(kind, W, bias)], scales[i] = WEIGHT_SCALE of
+        layer i where it is a graph layer (default 120, the header's)."""
+        n = len(layers)
+        kinds = (C.c_int * n)(*[int(k) for k, _, _ in layers])
+        rows, cols = (C.c_int * n)(), (C.c_int * n)()
+        Wp, bp = (_f32p * n)(), (_f32p * n)()
+        sc = np.ascontiguousarray(scales if scales is not None else [120.0] * n, np.float32)
+        keep = []
+        for i, (k, W, b) in enumerate(layers):
+            if k == LINEAR:
+                W = np.ascontiguousarray(W, np.float32)
+                b = np.ascontiguousarray(b, np.float32).ravel()
+                rows[i], cols[i] = W.shape
+                Wp[i], bp[i] = W.ctypes.data_as(_f32p), b.ctypes.data_as(_f32p)
+                keep += [W, b]
+        return self.L.ref_model_build(n, kinds, rows, cols, Wp, bp, _p(sc, _f32p))
+
+    def predict_on_as_is(self, h, gh, x):
+        """predict on a resident graph WITHOUT touching the model's weight scales."""
+        n = self.graph_size(gh)
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty(n, np.float32)
+        sec = C.c_double()
+        rc = self.L.ref_predict_on(h, gh, _p(x, _f32p), _p(out, _f32p), 1, C.byref(sec))
+        assert rc == 0 or n == 0
+        self.last_seconds = sec.value
+        return out
 
     def model_text(self, h) -> str:
         n = self.L.ref_model_text(h, None, 0)
@@ -243,6 +307,48 @@ class Reference:
             return out, (rp, col, nw)
         return out
 
+    # -- a graph that lives across calls (as GNN_VC's does) ---------------------------------------
+    REMOVE_NODE, REMOVE_NEIGHBORHOOD, FOLD_NEIGHBORHOOD, FOLD_TWIN, FOLD_ISOLATED, RELABEL, UNDO = range(7)
+
+    def graph_create(self, n, eu, ev, weights):
+        eu = np.ascontiguousarray(eu, np.uint32)
+        ev = np.ascontiguousarray(ev, np.uint32)
+        weights = np.ascontiguousarray(weights, np.uint32)
+        return self.L.ref_graph_create(n, len(eu), _p(eu, _u32p), _p(ev, _u32p), _p(weights, _u32p))
+
+    def graph_destroy(self, gh):
+        self.L.ref_graph_destroy(gh)
+
+    def graph_size(self, gh) -> int:
+        return int(self.L.ref_graph_size(gh))
+
+    def graph_mutate(self, gh, op: int, u: int = 0, v: int = 0) -> bool:
+        """One reduction_graph mutator (see REMOVE_NODE ...); False if its precondition does not hold."""
+        return self.L.ref_graph_mutate(gh, op, u, v) == 0
+
+    def graph_csr(self, gh):
+        """(row_ptr u64, col u32, W u32, NW u32, active u8) as predict reads them: begin/end/W/NW."""
+        n = self.graph_size(gh)
+        nnz = int(self.L.ref_graph_csr(gh, None, None, None, None, None))
+        rp, col = np.empty(n + 1, np.uint64), np.empty(max(nnz, 1), np.uint32)
+        w, nw, act = np.empty(max(n, 1), np.uint32), np.empty(max(n, 1), np.uint32), np.empty(max(n, 1), np.uint8)
+        self.L.ref_graph_csr(gh, _p(rp, _u64p), _p(col, _u32p), _p(w, _u32p), _p(nw, _u32p),
+                             act.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return rp, col[:nnz], w[:n], nw[:n], act[:n]
+
+    def predict_on(self, h, gh, x, scale, reps=1):
+        """model::predict on the resident graph; wall time of predict() alone in self.last_seconds."""
+        self.L.ref_model_set_weight_scale(h, float(scale))
+        n = self.graph_size(gh)
+        x = np.ascontiguousarray(x, np.float32)
+        assert x.size == n
+        out = np.empty(n, np.float32)
+        sec = C.c_double()
+        rc = self.L.ref_predict_on(h, gh, _p(x, _f32p), _p(out, _f32p), reps, C.byref(sec))
+        assert rc == 0 or n == 0, "predict returned an unexpected shape"
+        self.last_seconds = sec.value
+        return out
+
     def graph_layer(self, n, eu, ev, weights, scale, x):
         x = np.ascontiguousarray(x, np.float32)
         w = x.shape[1]
@@ -274,6 +380,16 @@ class Reference:
         x = np.ascontiguousarray(x, np.float32).ravel()
         out = np.empty_like(x)
         self.L.ref_sigmoid(x.size, _p(x, _f32p), _p(out, _f32p))
+        return out
+
+    def dot(self, A, B, C0=None, at=False, bt=False, beta=0.0):
+        """The reference's dot(): C = op(A) op(B) + beta C0 (A, B as stored: transposed when the flag is set)."""
+        A = np.ascontiguousarray(A, np.float32)
+        B = np.ascontiguousarray(B, np.float32)
+        m, k = (A.shape[1], A.shape[0]) if at else A.shape
+        n = B.shape[0] if bt else B.shape[1]
+        out = np.zeros((m, n), np.float32) if C0 is None else np.ascontiguousarray(C0, np.float32).copy()
+        self.L.ref_dot(int(at), int(bt), m, n, k, _p(A, _f32p), _p(B, _f32p), float(beta), _p(out, _f32p))
         return out
 
     def linear_init(self, K, Nout, seed):

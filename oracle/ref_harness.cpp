@@ -68,6 +68,37 @@ void *ref_model_create(const char *text) {
     return s;
 }
 
+// A model assembled in code, as old_files' training tools do (model(name), add_layer, the layer
+// structs' public members; src/gnn_inference.cpp:54-59): kinds[i] in the order of gnn::component's
+// alternatives (0 linear, 1 graph, 2 ReLU, 3 sigmoid); linear layers take rows[i] x cols[i] weights
+// W[i] and cols[i] bias values; graph layers take their own WEIGHT_SCALE scales[i] (the one thing
+// set_weight_scale cannot express: different scales per layer).
+void *ref_model_build(int n, const int *kinds, const int *rows, const int *cols, const float *const *W,
+                      const float *const *bias, const float *scales) {
+    auto *s = new ref_state();
+    s->m = gnn::model("built");
+    for (int i = 0; i < n; i++) {
+        switch (kinds[i]) {
+        case 0: {
+            gnn::linear_layer l(rows[i], cols[i], 0);
+            std::copy(W[i], W[i] + (size_t)rows[i] * cols[i], l.W.raw().begin());
+            std::copy(bias[i], bias[i] + cols[i], l.bias.raw().begin());
+            s->m.add_layer(l);
+            break;
+        }
+        case 1: {
+            gnn::graph_layer gl;
+            gl.WEIGHT_SCALE = scales[i];
+            s->m.add_layer(gl);
+            break;
+        }
+        case 2: s->m.add_layer(gnn::ReLU()); break;
+        default: s->m.add_layer(gnn::sigmoid()); break;
+        }
+    }
+    return s;
+}
+
 void ref_model_destroy(void *h) { delete static_cast<ref_state *>(h); }
 
 void ref_model_set_weight_scale(void *h, float ws) { static_cast<ref_state *>(h)->m.set_weight_scale(ws); }
@@ -122,6 +153,83 @@ int ref_predict(void *h, uint32_t n, uint64_t n_edges, const uint32_t *eu, const
     return 0;
 }
 
+// ---- a graph that lives across calls ------------------------------------------------------------
+// GNN_VC builds its graph once (src/GNN_VC.cpp:265) and calls predict on it again and again while
+// the reductions shrink it (:171-192).  bench.py's reference arm and the drop-in's end-to-end leg
+// time predict() alone on such a resident graph; the tests mutate it through the reference's own
+// reduction_graph members (include/reduction_graph.hpp:248-587) to get the holes, rotated lists,
+// appended fold vertices and relabelled ids that predict sees inside a real run.
+struct ref_graph_state {
+    reduction_graph<uint32_t, uint32_t> g;
+    matrix in, res;
+};
+
+void *ref_graph_create(uint32_t n, uint64_t n_edges, const uint32_t *eu, const uint32_t *ev, const uint32_t *w) {
+    return new ref_graph_state{make_graph(n, n_edges, eu, ev, w), matrix(), matrix()};
+}
+
+void ref_graph_destroy(void *gh) { delete static_cast<ref_graph_state *>(gh); }
+
+uint32_t ref_graph_size(void *gh) { return static_cast<ref_graph_state *>(gh)->g.size(); }
+
+// op: 0 remove_node(u)  1 remove_neighborhood(u)  2 fold_neighborhood(u)  3 fold_twin(u, v)
+//     4 fold_isolated(u)  5 relable_graph()  6 actions_pop() (undo the last one)
+// Preconditions are the reference's (asserts are compiled out): returns -1 instead of calling when
+// u/v are out of range or inactive, or when the fold's own precondition does not hold.
+int ref_graph_mutate(void *gh, int op, uint32_t u, uint32_t v) {
+    auto &g = static_cast<ref_graph_state *>(gh)->g;
+    auto ok = [&](uint32_t a) { return a < g.size() && g.is_active(a); };
+    switch (op) {
+    case 0: if (!ok(u)) return -1; g.remove_node(u); return 0;
+    case 1: if (!ok(u)) return -1; g.remove_neighborhood(u); return 0;
+    case 2: if (!ok(u) || !g.has_independent_neighbors(u) || g.NW(u) <= g.W(u)) return -1; g.fold_neighborhood(u); return 0;
+    case 3: if (!ok(u) || !ok(v) || !g.is_twin(u, v)) return -1; g.fold_twin(u, v); return 0;
+    case 4: if (!ok(u) || !g.is_isolated(u)) return -1; g.fold_isolated(u); return 0;
+    case 5: g.relable_graph(); return 0;
+    case 6: if (g.get_timestamp() == 0) return -1; g.actions_pop(); return 0;
+    default: return -2;
+    }
+}
+
+// The graph as predict sees it: through size(), begin(u)/end(u), W, NW only.  Pass nulls to get the
+// sizes first (returns nnz).  Inactive vertices (before a relabel) are reported with active[u] = 0.
+uint64_t ref_graph_csr(void *gh, uint64_t *row_ptr, uint32_t *col, uint32_t *w, uint32_t *nw, uint8_t *active) {
+    auto &g = static_cast<ref_graph_state *>(gh)->g;
+    uint64_t p = 0;
+    for (uint32_t u = 0; u < g.size(); u++) {
+        if (row_ptr) row_ptr[u] = p;
+        for (auto it = g.begin(u); it != g.end(u); ++it, ++p)
+            if (col) col[p] = *it;
+        if (w) w[u] = g.W(u);
+        if (nw) nw[u] = g.NW(u);
+        if (active) active[u] = g.is_active(u) ? 1 : 0;
+    }
+    if (row_ptr) row_ptr[g.size()] = p;
+    return p;
+}
+
+// model::predict on the resident graph; x and out have g.size() entries.  Wall time of predict() alone
+// (best of reps) in *seconds.
+int ref_predict_on(void *h, void *gh, const float *x, float *out, int reps, double *seconds) {
+    auto *s = static_cast<ref_state *>(h);
+    auto *gs = static_cast<ref_graph_state *>(gh);
+    const uint32_t n = gs->g.size();
+    gs->in.resize(n, 1);
+    for (uint32_t u = 0; u < n; u++) gs->in(u, 0) = x[u];
+    double best = 1e300;
+    if (reps < 1) reps = 1;
+    for (int r = 0; r < reps; r++) {
+        auto t0 = std::chrono::steady_clock::now();
+        s->m.predict(gs->in, gs->res, gs->g);
+        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (dt < best) best = dt;
+    }
+    if (seconds) *seconds = best;
+    if (gs->res.get_height() != n || (n && gs->res.get_width() != 1)) return -1;
+    for (uint32_t u = 0; u < n; u++) out[u] = gs->res(u, 0);
+    return 0;
+}
+
 // graph_layer::forward alone: in n x w  ->  out n x (2w+3)
 int ref_graph_layer(uint32_t n, uint64_t n_edges, const uint32_t *eu, const uint32_t *ev,
                     const uint32_t *w, float scale, const float *in, int width, float *out) {
@@ -159,6 +267,17 @@ void ref_sigmoid(size_t n, const float *in, float *out) {
     std::copy(in, in + n, a.raw().begin());
     gnn::sigmoid().forward(a, b);
     std::copy(b.raw().begin(), b.raw().end(), out);
+}
+
+// dot() itself (include/matrix.hpp:49, src/matrix.cpp:106-122): C = op(A) op(B) + beta C.
+// A is stored (at ? k x m : m x k), B (bt ? n x k : k x n), C m x n; all row-major.
+void ref_dot(int at, int bt, size_t m, size_t n, size_t k, const float *A, const float *B, float beta, float *Cio) {
+    matrix a(at ? k : m, at ? m : k), b(bt ? n : k, bt ? k : n), c(m, n);
+    std::copy(A, A + m * k, a.raw().begin());
+    std::copy(B, B + k * n, b.raw().begin());
+    std::copy(Cio, Cio + m * n, c.raw().begin());
+    dot(a, b, c, at != 0, bt != 0, beta);
+    std::copy(c.raw().begin(), c.raw().end(), Cio);
 }
 
 // linear_layer random init (gnn_inference.cpp:7-18), for API-parity tests of

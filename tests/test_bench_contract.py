@@ -15,7 +15,8 @@ KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_
 def test_reference_arm_prints_one_json_line():
     if not (ROOT / "oracle" / "_ref" / "libgnnref.so").exists() and not (ROOT / "oracle" / "_build" / "libgnnoracle.so").exists():
         pytest.skip("neither the compiled reference nor the oracle is built")
-    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--scale", "14"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -27,6 +28,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "sample" in d["cpu_baseline"] and "workload" in d["config"]
+    assert d["config"]["workload"] == "rmat_scale14_ef16" and d["config"]["edges"] > 0   # the arm's own config, not a stand-in
+    assert d["cpu_baseline"]["blas_kernel"]                                              # which OpenBLAS kernel set was timed
 
 
 def test_our_arm_refuses_to_run_without_a_gpu():

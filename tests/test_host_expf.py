@@ -36,3 +36,10 @@ def test_expf_bit_identical_to_libm(tmp_path):
                            str(c), "-o", str(exe), "-lm"])
     tot, bad = map(int, subprocess.check_output([str(exe)]).split())
     assert tot > 20_000_000 and bad == 0
+
+
+def test_expf_table_is_reproducible():
+    """The 32 constants exact mode depends on come out of tools/make_expf_table.py (60-digit 2^(i/32),
+    correctly rounded to binary64), entry for entry."""
+    import sys
+    subprocess.check_call([sys.executable, str(ROOT / "tools" / "make_expf_table.py"), "--check"])

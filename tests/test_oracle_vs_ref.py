@@ -45,3 +45,46 @@ def test_linear_init_matches(reference):
     W, b = reference.linear_init(5, 32, 7)
     lim = 1.0 / np.sqrt(6.0)
     assert W.shape == (5, 32) and np.all(np.abs(W) <= lim) and np.all(np.abs(b) <= lim)
+
+
+def test_dot_any_shape(reference, oracle):
+    """dot() for every OpenBLAS block class (rows 4/2/1 x columns 8/4/2/1), transposes, beta, and k long
+    enough to be cut into blocks of 128: the restatement equals the reference bit for bit."""
+    rng = np.random.default_rng(5)
+
+    def wide(shape):
+        return (np.exp(rng.uniform(-6, 6, shape)) * rng.choice([-1, 1], shape)).astype(np.float32)
+    for m in (1, 2, 3, 4, 5, 6, 7, 9, 64, 101):
+        for n in (1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 35):
+            for k in (1, 7, 16, 35, 47, 300):
+                at, bt = bool(rng.integers(2)), bool(rng.integers(2))
+                beta = float(rng.choice([0.0, 1.0, -0.75]))
+                A, B, C0 = wide((m, k)), wide((k, n)), wide((m, n))
+                As = A.T.copy() if at else A
+                Bs = B.T.copy() if bt else B
+                assert_bit_equal(oracle.dot(As, Bs, C0, at, bt, beta), reference.dot(As, Bs, C0, at, bt, beta),
+                                 f"{m}x{n}x{k} at={at} bt={bt} beta={beta}")
+    A, B = wide((35, 2500)), wide((2500, 32))                   # the weight-gradient shape of old_files' training
+    assert_bit_equal(oracle.dot(A, B), reference.dot(A, B), "k = 2500")
+
+
+def test_reduction_mutators_keep_the_oracle_in_step(reference, oracle, oracle_model, model_layers):
+    """predict on graphs that real reduction_graph mutators produced (fresh random scripts, not the
+    committed ones): restatement == reference."""
+    import random
+    hr = reference.model(po.layers_to_text(model_layers))
+    g = graphs.er_graph(2500, 9000, seed=77)
+    eu, ev = g.edges_numpy()
+    gh = reference.graph_create(g.n, eu, ev, g.numpy()[2])
+    rnd = random.Random(3)
+    for _ in range(4):
+        for _ in range(300):
+            reference.graph_mutate(gh, rnd.choice([0, 1, 2, 2, 4]), rnd.randrange(reference.graph_size(gh)))
+        reference.graph_mutate(gh, reference.RELABEL)
+        rp, col, w, nw, act = reference.graph_csr(gh)
+        assert act.all()
+        x = w.astype(np.float32) / np.float32(200.0)
+        want = reference.predict_on(hr, gh, x, 200.0)
+        if reference.graph_size(gh):
+            assert_bit_equal(oracle.predict(oracle_model, rp, col, w, nw, x, 200.0)[:, 0], want, "after reductions")
+    reference.graph_destroy(gh)

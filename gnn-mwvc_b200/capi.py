@@ -35,6 +35,7 @@ SIGNATURES = {
     "gvc_graph_upload_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
     "gvc_graph_staging": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(_u64p), C.POINTER(_u32p),
                                     C.POINTER(_u32p), C.POINTER(_u32p)]),
+    "gvc_graph_upload_stream": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "gvc_graph_adopt_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gvc_graph_set_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "gvc_peer_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
@@ -180,6 +181,28 @@ class Context:
         self._check(self.lib.gvc_graph_upload_shard(self.h, n_global, v_begin, v_end, _ptr(row_ptr, _u64p),
                                                     _ptr(col, _u32p), _ptr(W, _u32p), _ptr(NW, _u32p)))
         self.n_global, self.v_begin, self.v_end = n_global, v_begin, v_end
+
+    def graph_upload_ranges(self, span, begin, end, W, NW, n_threads: int = 0):
+        """gvc_graph_upload_stream from numpy arrays: `span` is the raw edge array (holes allowed),
+        begin/end the per-vertex ranges into it.  The callbacks copy slices into libgvc's pinned slots
+        (possibly from several of its worker threads)."""
+        span = _np(span, np.uint32)
+        begin, end = _np(begin, np.uint32), _np(end, np.uint32)
+        W, NW = _np(W, np.uint32), _np(NW, np.uint32)
+        n = len(begin)
+        FV = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p, _u32p)
+        FS = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint64, _u32p)
+
+        def fill_vertices(_user, first, count, b, e, w, nw):
+            for dst, src in ((b, begin), (e, end), (w, W), (nw, NW)):
+                np.ctypeslib.as_array(dst, shape=(count,))[:] = src[first:first + count]
+
+        def fill_span(_user, offset, count, dst):
+            np.ctypeslib.as_array(dst, shape=(count,))[:] = span[offset:offset + count]
+        fv, fs = FV(fill_vertices), FS(fill_span)
+        self._check(self.lib.gvc_graph_upload_stream(self.h, n, len(span), C.cast(fv, C.c_void_p), C.cast(fs, C.c_void_p),
+                                                     None, n_threads))
+        self.n_global, self.v_begin, self.v_end = n, 0, n
 
     def graph_staging(self, n_local: int, nnz: int):
         """Pinned host buffers of the context as numpy views (row_ptr u64, col, W, NW u32): fill

@@ -17,7 +17,9 @@
 #include <chrono>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gvc.h"
@@ -51,21 +53,58 @@ struct HostLayer {
     float *dW = nullptr, *db = nullptr;
 };
 
+// Device memory of a context comes out of a few big chunks (one cudaMalloc per chunk, bump
+// allocation, nothing is returned before the context goes): a first predict() then pays for ONE
+// allocation sized for its graph instead of twenty (cudaMalloc costs up to a millisecond each, and
+// GNN_VC's first graph is its largest).  Buffers that outgrow their place move to a new one; the
+// old place stays unused until the context is destroyed (graphs shrink in a solver run).
+struct Arena {
+    struct Chunk { char *p; size_t size, used; };
+    std::vector<Chunk> chunks;
+    size_t next_chunk = 0;                 // hint: size of the next chunk (set before a burst of reservations)
+    void *alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (!chunks.empty()) {
+            Chunk &c = chunks.back();
+            if (c.size - c.used >= bytes) { void *r = c.p + c.used; c.used += bytes; return r; }
+        }
+        size_t want = std::max(std::max(bytes, next_chunk), (size_t)8 << 20);    // small requests share a chunk
+        next_chunk = 0;
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess && want > bytes) { cudaGetLastError(); want = bytes; e = cudaMalloc(&p, want); }
+        if (e != cudaSuccess) { fail(GVC_ERR_ALLOC, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e)); return nullptr; }
+        chunks.push_back({static_cast<char *>(p), want, bytes});
+        return p;
+    }
+    void release_all() {
+        for (auto &c : chunks) cudaFree(c.p);
+        chunks.clear();
+    }
+};
+thread_local Arena *tl_arena = nullptr;    // the arena of the context an entry point works on (use_device)
+
 template <typename T>
 struct DevBuf {   // grow-only device buffer
     T *p = nullptr;
     size_t cap = 0;
+    bool own = false;                      // allocated with cudaMalloc (no arena at hand), freed on release
     int reserve(size_t n) {
         if (n <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        release();
         size_t want = n + n / 8 + 64;
-        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
-        if (e != cudaSuccess) return fail(GVC_ERR_ALLOC, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+        if (tl_arena) {
+            p = static_cast<T *>(tl_arena->alloc(want * sizeof(T)));
+            if (!p) return GVC_ERR_ALLOC;
+        } else {
+            cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+            if (e != cudaSuccess) { p = nullptr; return fail(GVC_ERR_ALLOC, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e)); }
+            own = true;
+        }
         cap = want;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && own) cudaFree(p); p = nullptr; cap = 0; own = false; }
 };
 
 template <typename T>
@@ -102,6 +141,7 @@ struct Tracer {
 }  // namespace
 
 struct gvc_ctx {
+    Arena arena;                         // all DevBufs below live in it
     int device = 0;
     cudaStream_t stream = nullptr;       // where work is enqueued (own_stream unless gvc_set_stream)
     cudaStream_t own_stream = nullptr;
@@ -125,6 +165,15 @@ struct gvc_ctx {
     DevBuf<uint32_t> d_flag;             // upload validation result (kBadRowPtr | kBadCol)
     PinBuf<uint64_t> stg_row_ptr;        // gvc_graph_staging: pinned host buffers the caller fills
     PinBuf<uint32_t> stg_col, stg_W, stg_NW;
+    // gvc_graph_upload_stream: the graph as the host holds it (one edge array with holes + a range per
+    // vertex) goes through a small ring of pinned slots, filled by worker threads through the caller's
+    // callbacks while earlier slots are in flight; the packed CSR is built on the device
+    PinBuf<unsigned char> ring;          // n_slots x slot_bytes
+    size_t slot_bytes = 0;
+    int n_slots = 0;
+    std::vector<cudaEvent_t> slot_ev;    // slot's last copy has left the host buffer
+    DevBuf<uint32_t> d_span, d_rb, d_re; // raw edge span, per-vertex [begin, end) into it
+    DevBuf<uint64_t> d_blk;              // block sums of the degree scan (+ the total at the end)
     cudaStream_t copy_stream = nullptr;  // the adjacency travels here while the schedule is built on `stream`
     cudaEvent_t ev_begin = nullptr, ev_copy = nullptr;
     // schedule (gvc_kernels.cuh): vertices counting-sorted by degree bin + tile classes
@@ -524,6 +573,145 @@ int build_schedule(gvc_ctx *c) {
     return 0;
 }
 
+// ---- packed CSR from ranges into a raw edge span (gvc_graph_upload_stream) --------------------------
+constexpr uint32_t kBadRange = 4u;
+constexpr int kScanItems = 4096;          // vertices per CTA of the degree scan (256 threads x 16)
+
+// degree of vertex u, and the range check: begin <= end <= span_len
+__device__ __forceinline__ uint32_t range_degree(const uint32_t *__restrict__ rb, const uint32_t *__restrict__ re,
+                                                 uint32_t u, uint64_t span_len, bool &bad) {
+    const uint32_t b = rb[u], e = re[u];
+    if (b > e || e > span_len) { bad = true; return 0u; }
+    return e - b;
+}
+
+__global__ void __launch_bounds__(256)
+range_block_sums_kernel(const uint32_t *__restrict__ rb, const uint32_t *__restrict__ re, uint32_t n, uint64_t span_len,
+                        uint64_t *__restrict__ blk, uint32_t *__restrict__ flag) {
+    __shared__ uint64_t part[8];
+    const uint32_t base = blockIdx.x * kScanItems;
+    bool bad = false;
+    uint64_t sum = 0;
+    for (int t = 0; t < 16; ++t) {
+        const uint32_t u = base + t * 256 + threadIdx.x;
+        if (u < n) sum += range_degree(rb, re, u, span_len, bad);
+    }
+    for (int m = 16; m; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t s = 0;
+        for (int w = 0; w < 8; ++w) s += part[w];
+        blk[blockIdx.x] = s;
+    }
+    if (bad) atomicOr(flag, kBadRange);
+}
+
+// exclusive scan of the block sums in place, one CTA; blk[nb] receives the total
+__global__ void __launch_bounds__(1024)
+range_scan_blocks_kernel(uint64_t *__restrict__ blk, uint32_t nb) {
+    __shared__ uint64_t part[1024];
+    const uint32_t per = (nb + 1023) / 1024;
+    const uint32_t lo = min(nb, threadIdx.x * per), hi = min(nb, lo + per);
+    uint64_t s = 0;
+    for (uint32_t i = lo; i < hi; ++i) s += blk[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (int t = 0; t < 1024; ++t) { const uint64_t v = part[t]; part[t] = run; run += v; }
+        blk[nb] = run;
+    }
+    __syncthreads();
+    uint64_t run = part[threadIdx.x];
+    for (uint32_t i = lo; i < hi; ++i) { const uint64_t v = blk[i]; blk[i] = run; run += v; }
+}
+
+// row_ptr[u] = exclusive prefix of the degrees (32-bit: the caller has checked the total)
+__global__ void __launch_bounds__(256)
+range_row_ptr_kernel(const uint32_t *__restrict__ rb, const uint32_t *__restrict__ re, uint32_t n, uint64_t span_len,
+                     const uint64_t *__restrict__ blk, uint32_t *__restrict__ row_ptr) {
+    __shared__ uint32_t warp_sum[8];
+    const uint32_t base = blockIdx.x * kScanItems + threadIdx.x * 16;      // 16 consecutive vertices per thread
+    bool bad = false;
+    uint32_t d[16], s = 0;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) { d[t] = (base + t < n) ? range_degree(rb, re, base + t, span_len, bad) : 0u; s += d[t]; }
+    uint32_t inc = s;                                                      // inclusive scan over the CTA's threads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int m = 1; m < 32; m <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, m); if (lane >= m) inc += v; }
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    uint32_t off = (uint32_t)blk[blockIdx.x];
+    for (int w = 0; w < warp; ++w) off += warp_sum[w];
+    uint32_t run = off + inc - s;
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+        if (base + t < n) { row_ptr[base + t] = run; run += d[t]; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) row_ptr[n] = (uint32_t)blk[gridDim.x];
+}
+
+// col[packed offset + i] = span[begin[u] + i], by degree class of the schedule (a list of 64 452 entries
+// and a list of 3 must not cost the same): warp tasks, grid-strided --
+//   ring vertices (deg >= 2048)  their 4096-entry chunks (the fast-mode chunk list), 512 entries per warp task
+//   mid vertices (64 <= deg)     one warp per vertex
+//   the rest                     32 vertices per warp, their short lists copied one after the other
+// vrec[pos] = {id, packed begin, packed end, W}.  Every id is checked against n_global on the way.
+__global__ void __launch_bounds__(256)
+range_compact_kernel(const uint32_t *__restrict__ span, const uint32_t *__restrict__ rb, const uint4 *__restrict__ vrec,
+                     const uint4 *__restrict__ ring_chunk, uint32_t n_ring_chunks, uint32_t n_ring, uint32_t n_mid,
+                     uint32_t n_local, uint32_t n_global, uint32_t *__restrict__ col, uint32_t *__restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t t_ring = n_ring_chunks * 8u, t_mid = n_mid, n_low = n_local - n_ring - n_mid;
+    const uint32_t n_tasks = t_ring + t_mid + (n_low + 31) / 32;
+    bool bad = false;
+    auto copy = [&](uint32_t src, uint32_t dst, uint32_t len) {
+        for (uint32_t i = lane; i < len; i += 32) {
+            const uint32_t id = __ldcs(span + src + i);
+            bad |= id >= n_global;
+            col[dst + i] = id;
+        }
+    };
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tasks; t += warps) {
+        if (t < t_ring) {
+            const uint4 ck = __ldg(ring_chunk + (t >> 3));                 // {pos, packed first, packed end, chunk}
+            const uint4 r = __ldg(vrec + ck.x);
+            const uint32_t lo = ck.y + (t & 7u) * 512u, hi = min(ck.z, lo + 512u);
+            if (lo < hi) copy(__ldg(rb + r.x) + (lo - r.y), lo, hi - lo);
+        } else if (t < t_ring + t_mid) {
+            const uint4 r = __ldg(vrec + n_ring + (t - t_ring));
+            copy(__ldg(rb + r.x), r.y, r.z - r.y);
+        } else {
+            const uint32_t pos = n_ring + n_mid + (t - t_ring - t_mid) * 32u + lane;
+            uint4 r = make_uint4(0u, 0u, 0u, 0u);
+            uint32_t src = 0;
+            if (pos < n_local) { r = __ldg(vrec + pos); src = __ldg(rb + r.x); }
+            for (int v = 0; v < 32; ++v) {
+                const uint32_t s_v = __shfl_sync(0xffffffffu, src, v), d_v = __shfl_sync(0xffffffffu, r.y, v),
+                               l_v = __shfl_sync(0xffffffffu, r.z - r.y, v);
+                copy(s_v, d_v, l_v);
+            }
+        }
+    }
+    if (bad) atomicOr(flag, kBadCol);
+}
+
+// The ring of pinned slots (grow-only; sized once for the first, largest graph of a GNN_VC run).
+int ensure_ring(gvc_ctx *c, int n_slots, size_t slot_bytes) {
+    if (c->n_slots >= n_slots && c->slot_bytes >= slot_bytes) return 0;
+    for (auto &e : c->slot_ev) cudaEventDestroy(e);
+    c->slot_ev.clear();
+    c->ring.release();
+    c->n_slots = 0; c->slot_bytes = 0;
+    int rc;
+    if ((rc = c->ring.reserve((size_t)n_slots * slot_bytes))) return rc;
+    c->slot_ev.resize(n_slots);
+    for (auto &e : c->slot_ev) GVC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->n_slots = n_slots; c->slot_bytes = slot_bytes;
+    return 0;
+}
+
 template <int STAGE>
 int set_stage_attrs(gvc_ctx *c) {
     const int smem = (int)stage_smem_bytes<STAGE>();
@@ -543,7 +731,16 @@ int check_ctx(const gvc_ctx *c) {
 
 int use_device(const gvc_ctx *c) {
     GVC_CUDA(cudaSetDevice(c->device));
+    tl_arena = &const_cast<gvc_ctx *>(c)->arena;
     return 0;
+}
+
+// Before the first big burst of reservations: one chunk for everything a graph of n vertices and
+// `entries` adjacency entries needs (offsets, ids twice while a streamed upload compacts them, weights,
+// schedule, x, h1, h2, scores, feature vectors of the high-degree vertices).
+void arena_hint(gvc_ctx *c, uint64_t n, uint64_t entries) {
+    if (!c->arena.chunks.empty()) return;
+    c->arena.next_chunk = (size_t)(n * 216 + entries * 9 + (4u << 20));
 }
 
 int ensure_activations(gvc_ctx *c) {
@@ -679,6 +876,9 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     for (auto &p : c->d_stage_params) if (p) cudaFree(p);
     c->own_row_ptr.release(); c->own_col.release(); c->own_W.release(); c->own_NW.release();
     c->d_row_ptr64.release(); c->d_flag.release();
+    c->d_span.release(); c->d_rb.release(); c->d_re.release(); c->d_blk.release();
+    for (auto &e : c->slot_ev) cudaEventDestroy(e);
+    c->ring.release();
     c->stg_row_ptr.release(); c->stg_col.release(); c->stg_W.release(); c->stg_NW.release();
     c->d_order.release(); c->d_vrec.release(); c->d_bins.release(); c->d_sync.release(); c->d_feat.release();
     c->d_peer_mask.release();
@@ -687,6 +887,8 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
     c->d_ping.release(); c->d_pong.release();
     c->pin_x.release(); c->pin_scores.release();
+    c->arena.release_all();
+    tl_arena = nullptr;
     cudaEventDestroy(c->ev_begin);
     cudaEventDestroy(c->ev_copy);
     cudaStreamDestroy(c->copy_stream);
@@ -775,6 +977,7 @@ int gvc_graph_upload_shard(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
     if (nnz >= (1ull << 32)) return fail(GVC_ERR_UNSUPPORTED, "shard has %llu adjacency entries; 2^32 is the limit", (unsigned long long)nnz);
     if (nnz && !col) return fail(GVC_ERR_ARG, "null col");
     Tracer tr;
+    arena_hint(c, std::max<uint64_t>(nl, n_global / 2), nnz);
     if ((rc = c->own_row_ptr.reserve((size_t)nl + 1))) return rc;
     if ((rc = c->own_col.reserve(nnz + 4))) return rc;      // readable up to the next multiple of four ids
     if ((rc = c->own_W.reserve(nl))) return rc;
@@ -837,6 +1040,129 @@ int gvc_graph_upload_shard(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
     if (flag) {
         c->have_graph = false;
         return fail(GVC_ERR_ARG, "a neighbour id is >= %u vertices", n_global);
+    }
+    return 0;
+}
+
+int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_vertices_fn fill_vertices,
+                            gvc_fill_span_fn fill_span, void *user, int n_threads) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (n && !fill_vertices) return fail(GVC_ERR_ARG, "null vertex callback");
+    if (span_len && !fill_span) return fail(GVC_ERR_ARG, "null span callback");
+    if (span_len >= (1ull << 32)) return fail(GVC_ERR_UNSUPPORTED, "edge span of %llu entries; 2^32 is the limit", (unsigned long long)span_len);
+    if ((rc = use_device(c))) return rc;
+    Tracer tr;
+    c->have_graph = false;
+    // work items: vertex chunks (4 arrays of kVChunk uint32 = one slot) and span chunks (one slot each)
+    constexpr uint32_t kVChunk = 16384;                  // 4 x 64 KB
+    constexpr size_t kSlotBytes = 4 * (size_t)kVChunk * sizeof(uint32_t);      // 256 KB
+    constexpr uint64_t kSChunk = kSlotBytes / sizeof(uint32_t);
+    const uint64_t n_vchunks = ((uint64_t)n + kVChunk - 1) / kVChunk, n_schunks = (span_len + kSChunk - 1) / kSChunk;
+    const uint64_t n_items = n_vchunks + n_schunks;
+    int workers = n_threads > 0 ? n_threads : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    workers = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)workers, (n_items + 3) / 4));   // >= 4 items per thread
+    if ((rc = ensure_ring(c, std::max(2 * workers, 16), kSlotBytes))) return rc;
+    arena_hint(c, n, span_len);
+    if ((rc = c->d_rb.reserve(n))) return rc;
+    if ((rc = c->d_re.reserve(n))) return rc;
+    if ((rc = c->own_W.reserve(n))) return rc;
+    if ((rc = c->own_NW.reserve(n))) return rc;
+    if ((rc = c->own_row_ptr.reserve((size_t)n + 1))) return rc;
+    if ((rc = c->d_span.reserve(span_len + 4))) return rc;
+    if ((rc = c->own_col.reserve(span_len + 4))) return rc;      // nnz <= span_len once the ranges are known good
+    if ((rc = c->d_flag.reserve(1))) return rc;
+    const uint32_t n_scan = (n + kScanItems - 1) / kScanItems;
+    if ((rc = c->d_blk.reserve((size_t)n_scan + 1))) return rc;
+    tr.tick("stream: buffers");
+    GVC_CUDA(cudaMemsetAsync(c->d_flag.p, 0, sizeof(uint32_t), c->stream));
+    GVC_CUDA(cudaEventRecord(c->ev_begin, c->stream));           // earlier forwards are done with the old arrays
+    GVC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_begin, 0));
+
+    // ---- host side: workers fill slots through the callbacks and send them off ------------------
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> err{0};
+    auto work = [&](int w) {
+        if (cudaSetDevice(c->device) != cudaSuccess) { err = 1; return; }
+        int turn = 0;
+        for (;;) {
+            const uint64_t it = next.fetch_add(1);
+            if (it >= n_items || err.load()) break;
+            const int slot = 2 * w + (turn++ & 1);
+            unsigned char *host = c->ring.p + (size_t)slot * c->slot_bytes;
+            if (cudaEventSynchronize(c->slot_ev[slot]) != cudaSuccess) { err = 1; break; }    // its last copy has left
+            cudaError_t e = cudaSuccess;
+            if (it < n_vchunks) {
+                const uint32_t first = (uint32_t)(it * kVChunk), cnt = std::min<uint32_t>(kVChunk, n - first);
+                uint32_t *b = reinterpret_cast<uint32_t *>(host), *en = b + kVChunk, *w_ = en + kVChunk, *nw = w_ + kVChunk;
+                fill_vertices(user, first, cnt, b, en, w_, nw);
+                e = cudaMemcpyAsync(c->d_rb.p + first, b, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_re.p + first, en, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(c->own_W.p + first, w_, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(c->own_NW.p + first, nw, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
+            } else {
+                const uint64_t off = (it - n_vchunks) * kSChunk, cnt = std::min<uint64_t>(kSChunk, span_len - off);
+                fill_span(user, off, cnt, reinterpret_cast<uint32_t *>(host));
+                e = cudaMemcpyAsync(c->d_span.p + off, host, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(c->slot_ev[slot], c->copy_stream);
+            if (e != cudaSuccess) { err = 1000 + (int)e; break; }
+        }
+    };
+    if (workers == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int w = 1; w < workers; ++w) th.emplace_back(work, w);
+        work(0);
+        for (auto &t : th) t.join();
+    }
+    if (err.load()) { cudaStreamSynchronize(c->copy_stream); return fail(err.load(), "streamed upload: a copy failed"); }
+    GVC_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
+    tr.tick("stream: fill + copies issued");
+
+    // ---- device side: degrees -> offsets, lists -> packed CSR, checks -----------------------------
+    GVC_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    uint64_t nnz = 0;
+    if (n) {
+        range_block_sums_kernel<<<n_scan, 256, 0, c->stream>>>(c->d_rb.p, c->d_re.p, n, span_len, c->d_blk.p, c->d_flag.p);
+        range_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(c->d_blk.p, n_scan);
+        GVC_CUDA(cudaGetLastError());
+        c->launches += 2;
+        uint32_t flag = 0;
+        GVC_CUDA(cudaMemcpyAsync(&nnz, c->d_blk.p + n_scan, sizeof(nnz), cudaMemcpyDeviceToHost, c->stream));
+        GVC_CUDA(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
+        GVC_CUDA(cudaStreamSynchronize(c->stream));
+        if (flag & kBadRange) return fail(GVC_ERR_ARG, "a vertex range is reversed or ends past the edge span");
+        if (nnz >= (1ull << 32)) return fail(GVC_ERR_UNSUPPORTED, "graph has %llu adjacency entries; 2^32 is the limit", (unsigned long long)nnz);
+        range_row_ptr_kernel<<<n_scan, 256, 0, c->stream>>>(c->d_rb.p, c->d_re.p, n, span_len, c->d_blk.p, c->own_row_ptr.p);
+        GVC_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    tr.tick("stream: offsets");
+    // the degree schedule needs offsets and weights only; the lists are then moved class by class
+    if ((rc = set_graph_views(c, n, 0, n, c->own_row_ptr.p, c->own_col.p, c->own_W.p, c->own_NW.p, nnz))) {
+        c->have_graph = false;
+        return rc;
+    }
+    tr.tick("stream: schedule");
+    if (nnz) {
+        const Schedule &sc = c->sched;
+        const uint64_t warp_tasks = (uint64_t)sc.n_chunks16 * 8 + sc.n_mid + (n - sc.n_ring - sc.n_mid + 31) / 32;
+        range_compact_kernel<<<(unsigned)std::min<uint64_t>(148 * 8, (warp_tasks + 7) / 8), 256, 0, c->stream>>>(
+            c->d_span.p, c->d_rb.p, c->d_vrec.p, c->d_hub_chunk[0].p, sc.n_chunks16, sc.n_ring, sc.n_mid, n, n,
+            c->own_col.p, c->d_flag.p);
+        GVC_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    if ((rc = build_peer_mask(c))) { c->have_graph = false; return rc; }
+    uint32_t flag = 0;
+    GVC_CUDA(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    tr.tick("stream: compaction");
+    if (flag) {
+        c->have_graph = false;
+        return fail(GVC_ERR_ARG, "a neighbour id is >= %u vertices", n);
     }
     return 0;
 }
@@ -1039,16 +1365,39 @@ int gvc_forward(gvc_ctx *c, const float *x, float scale, float *scores, int mode
     if (!x || !scores) return fail(GVC_ERR_ARG, "null buffer");
     if ((rc = use_device(c))) return rc;
     Tracer tr;
-    if ((rc = c->pin_x.reserve(n))) return rc;
-    if ((rc = c->pin_scores.reserve(n))) return rc;
-    tr.tick("forward: pinned x/scores");
-    std::memcpy(c->pin_x.p, x, (size_t)n * sizeof(float));
-    GVC_CUDA(cudaMemcpyAsync(c->d_x.p, c->pin_x.p, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    // x goes up and the scores come back through the ring of pinned slots (the same one the streamed
+    // graph upload uses): nothing of the graph's size is pinned per call
+    if ((rc = ensure_ring(c, 16, 256u << 10))) return rc;
+    const size_t per = c->slot_bytes / sizeof(float);
+    const size_t chunks = ((size_t)n + per - 1) / per;
+    for (size_t k = 0; k < chunks; ++k) {
+        const int slot = (int)(k % c->n_slots);
+        const size_t off = k * per, cnt = std::min(per, (size_t)n - off);
+        float *host = reinterpret_cast<float *>(c->ring.p + (size_t)slot * c->slot_bytes);
+        GVC_CUDA(cudaEventSynchronize(c->slot_ev[slot]));
+        std::memcpy(host, x + off, cnt * sizeof(float));
+        GVC_CUDA(cudaMemcpyAsync(c->d_x.p + off, host, cnt * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        GVC_CUDA(cudaEventRecord(c->slot_ev[slot], c->stream));
+    }
+    tr.tick("forward: x up");
     if ((rc = gvc_forward_device(c, c->d_x.p, scale, c->d_scores.p, mode))) return rc;
-    GVC_CUDA(cudaMemcpyAsync(c->pin_scores.p, c->d_scores.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    GVC_CUDA(cudaStreamSynchronize(c->stream));
-    tr.tick("forward: copies + kernels");
-    std::memcpy(scores, c->pin_scores.p, (size_t)n * sizeof(float));
+    for (size_t k0 = 0; k0 < chunks; k0 += c->n_slots) {           // as many chunks as there are slots per round
+        const size_t k1 = std::min(chunks, k0 + (size_t)c->n_slots);
+        for (size_t k = k0; k < k1; ++k) {
+            const int slot = (int)(k % c->n_slots);
+            const size_t off = k * per, cnt = std::min(per, (size_t)n - off);
+            GVC_CUDA(cudaMemcpyAsync(c->ring.p + (size_t)slot * c->slot_bytes, c->d_scores.p + off, cnt * sizeof(float),
+                                     cudaMemcpyDeviceToHost, c->stream));
+            GVC_CUDA(cudaEventRecord(c->slot_ev[slot], c->stream));
+        }
+        for (size_t k = k0; k < k1; ++k) {
+            const int slot = (int)(k % c->n_slots);
+            const size_t off = k * per, cnt = std::min(per, (size_t)n - off);
+            GVC_CUDA(cudaEventSynchronize(c->slot_ev[slot]));
+            std::memcpy(scores + off, c->ring.p + (size_t)slot * c->slot_bytes, cnt * sizeof(float));
+        }
+    }
+    tr.tick("forward: kernels + scores down");
     return 0;
 }
 

@@ -6,8 +6,9 @@
 // the same meaning, so src/GNN_VC.cpp (model parse :263, set_weight_scale :278,
 // predict :192) links and runs unchanged -- with the forward pass on a B200.
 //
-//   model::predict      -> CSR view of the reduction_graph through its public
-//                          accessors, then gvc_graph_upload + gvc_forward
+//   model::predict      -> the reduction_graph's edge span + per-vertex ranges, read through its
+//                          public accessors and streamed to the device (gvc_graph_upload_stream,
+//                          CSR built by kernels), then gvc_forward
 //   layer ::forward     -> the matching single-layer entry points of libgvc
 //   parse / print / add -> host code, same text format
 //
@@ -15,14 +16,19 @@
 #include "gnn_inference.hpp"
 
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 #include <algorithm>
 #include <string>
 #include <thread>
 #include <vector>
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
 
 #include "gvc.h"
 #include "gvc_host_ctx.hpp"
@@ -105,6 +111,162 @@ csr_view extract_csr(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g) {
         for (Tn u = a; u < b; ++u) std::copy(g.begin(u), g.end(u), s.col + s.row_ptr[u]);
     });
     return s;
+}
+
+// ---- the graph straight out of the reduction_graph -------------------------
+// begin(u)/end(u) are iterators into ONE edge vector (include/reduction_graph.hpp:30,692-704); between
+// two predicts the reductions rotate removed neighbours to the front of a list and skip them, append
+// fold vertices' lists at the end and relabel in place (:248-587).  So the live adjacency is "a span of
+// that vector + a range per vertex" -- and that is what goes to the device, through libgvc's ring of
+// pinned slots (gvc_graph_upload_stream): no compaction pass and no second copy on the host, nothing
+// pinned per graph; the packed CSR is built by kernels.  Only const accessors that do not write the
+// graph's cursor are used, so the callbacks may run on several threads.
+struct graph_reader {
+    const reduction_graph<Tn, Tw> *g;
+    std::vector<Tn>::const_iterator origin;     // begin(0): all offsets are taken relative to it
+    int64_t lo;                                 // smallest offset of a non-empty list = start of the span
+    const uint32_t *prefix;                     // gathered mode: prefix[u] = entries of the lists before u's (else null)
+};
+
+// Late in a run the live lists are a small part of the edge vector (ER 1M/5M: 4 540 live entries in a
+// span of 10.9 M at the last predict), early on they are nearly all of it.  Two ways to present the
+// graph to gvc_graph_upload_stream, chosen per call:
+//   span mode      the "edge span" IS the vector's live stretch [lo, hi): one straight copy, holes included
+//   gathered mode  the "edge span" is the concatenation of the lists in vertex order: only live entries
+//                  travel; offsets are prefix sums of the degrees
+void read_vertices(void *user, uint32_t first, uint32_t count, uint32_t *begin, uint32_t *end, uint32_t *W, uint32_t *NW) {
+    const graph_reader &r = *static_cast<const graph_reader *>(user);
+    for (uint32_t i = 0; i < count; ++i) {
+        const Tn u = first + i;
+        if (r.prefix) {
+            begin[i] = r.prefix[u];
+            end[i] = r.prefix[u + 1];
+        } else {
+            const auto b = r.g->begin(u), e = r.g->end(u);
+            const bool empty = b == e;
+            begin[i] = empty ? 0u : (uint32_t)((b - r.origin) - r.lo);
+            end[i] = empty ? 0u : (uint32_t)((e - r.origin) - r.lo);
+        }
+        W[i] = r.g->W(u);
+        NW[i] = r.g->NW(u);
+    }
+}
+
+// dst is a 64-byte aligned slot of pinned memory that the DMA engine reads next: written past the
+// caches (streaming stores), which also spares the read-for-ownership of a plain memcpy
+void copy_out(uint32_t *dst, const uint32_t *src, uint64_t count) {
+#if defined(__AVX2__)
+    uint64_t i = 0;
+    while (i < count && (reinterpret_cast<uintptr_t>(dst + i) & 31u)) { dst[i] = src[i]; ++i; }
+    for (; i + 8 <= count; i += 8)
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)));
+    for (; i < count; ++i) dst[i] = src[i];
+#else
+    std::memcpy(dst, src, count * sizeof(uint32_t));
+#endif
+}
+
+void read_span(void *user, uint64_t offset, uint64_t count, uint32_t *dst) {
+    const graph_reader &r = *static_cast<const graph_reader *>(user);
+    static_assert(sizeof(Tn) == sizeof(uint32_t), "ids are 32-bit");
+    if (!r.prefix) {
+        copy_out(dst, &*(r.origin + (r.lo + (int64_t)offset)), count);
+    } else {
+        // the vertex whose list holds entry `offset`, then list after list until `count` entries are out
+        const Tn n = r.g->size();
+        Tn u = (Tn)(std::upper_bound(r.prefix, r.prefix + n + 1, (uint32_t)offset) - r.prefix) - 1;
+        uint64_t skip = offset - r.prefix[u], left = count;
+        for (; left; ++u) {
+            const uint64_t len = (uint64_t)(r.prefix[u + 1] - r.prefix[u]);
+            if (len <= skip) { skip -= len; continue; }
+            const uint64_t take = std::min(left, len - skip);
+            copy_out(dst, &*(r.g->begin(u) + (int64_t)skip), take);
+            dst += take; left -= take; skip = 0;
+        }
+    }
+#if defined(__AVX2__)
+    _mm_sfence();
+#endif
+}
+
+// Upload g into the context; returns the number of entries that travelled (for the profile line).
+uint64_t upload_graph_streamed(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g) {
+    const Tn n = g.size();
+    graph_reader r{&g, n ? g.begin(0) : std::vector<Tn>::const_iterator(), 0, nullptr};
+    // where does the live part of the edge vector start and stop, and how much of it is live?
+    const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned nt = n < (1u << 17) ? 1u : std::min(8u, hw ? hw : 1u);
+    const Tn step = (n + nt - 1) / nt;
+    auto range_of = [&](unsigned t, Tn &a, Tn &b) {
+        a = (Tn)std::min<uint64_t>((uint64_t)t * step, n);
+        b = (Tn)std::min<uint64_t>((uint64_t)(t + 1) * step, n);
+    };
+    auto parallel = [&](auto &&fn) {
+        if (nt == 1) { fn(0u); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back([&fn, t] { fn(t); });
+        fn(0u);
+        for (auto &x : th) x.join();
+    };
+    std::vector<int64_t> lo(nt, INT64_MAX), hi(nt, INT64_MIN);
+    std::vector<uint64_t> live(nt, 0);
+    parallel([&](unsigned t) {
+        Tn a, b;
+        range_of(t, a, b);
+        int64_t l = INT64_MAX, h = INT64_MIN;
+        uint64_t cnt = 0;
+        for (Tn u = a; u < b; ++u) {
+            const auto bi = g.begin(u), ei = g.end(u);
+            if (bi == ei) continue;
+            l = std::min<int64_t>(l, bi - r.origin);
+            h = std::max<int64_t>(h, ei - r.origin);
+            cnt += (uint64_t)(ei - bi);
+        }
+        lo[t] = l; hi[t] = h; live[t] = cnt;
+    });
+    const int64_t l = *std::min_element(lo.begin(), lo.end()), h = *std::max_element(hi.begin(), hi.end());
+    uint64_t span_len = h > l ? (uint64_t)(h - l) : 0, nnz = 0;
+    for (uint64_t c : live) nnz += c;
+    r.lo = span_len ? l : 0;
+    static std::vector<uint32_t> prefix;          // gathered mode only; kept between calls
+    if (nnz < (1ull << 32) && nnz * 10 < span_len * 7) {
+        if (prefix.size() < (size_t)n + 1) prefix.resize((size_t)n + 1);
+        parallel([&](unsigned t) {
+            Tn a, b;
+            range_of(t, a, b);
+            uint64_t run = 0;
+            for (unsigned k = 0; k < t; ++k) run += live[k];
+            for (Tn u = a; u < b; ++u) { prefix[u] = (uint32_t)run; run += (uint64_t)(g.end(u) - g.begin(u)); }
+            if (b == n) prefix[n] = (uint32_t)run;
+        });
+        if (n == 0) prefix[0] = 0;
+        r.prefix = prefix.data();
+        span_len = nnz;
+    }
+    const int rc = gvc_graph_upload_stream(ctx, n, span_len, read_vertices, read_span, &r, 0);
+    if (rc != 0) gvc_host::die("gvc_graph_upload_stream", rc);
+    return span_len;
+}
+
+// GVC_UPLOAD=packed keeps the first implementation (CSR compacted on the host, gvc_graph_upload) for
+// comparison; default is the streamed path above.
+bool use_packed_upload() {
+    static const bool packed = [] { const char *e = std::getenv("GVC_UPLOAD"); return e && std::strcmp(e, "packed") == 0; }();
+    return packed;
+}
+
+void upload_graph(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g, uint64_t *entries, double *t_extract) {
+    if (!use_packed_upload()) {
+        *t_extract = 0;
+        *entries = upload_graph_streamed(ctx, g);
+        return;
+    }
+    const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    const csr_view s = extract_csr(ctx, g);
+    *t_extract = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
+    const int rc = gvc_graph_upload(ctx, g.size(), s.row_ptr, s.col, s.w, s.nw);
+    if (rc != 0) gvc_host::die("gvc_graph_upload", rc);
+    *entries = s.nnz;
 }
 
 // GVC_PROFILE=1: per-call and cumulative timing of predict() on stderr (CSR extraction on the
@@ -212,10 +374,10 @@ void graph_layer::forward(const matrix &in, matrix &out, const reduction_graph<T
     out.resize(n, 2 * w + 3);
     if (n == 0) return;
     gvc_ctx *ctx = gvc_host::context();
-    const csr_view s = extract_csr(ctx, g);
-    int rc = gvc_graph_upload(ctx, g.size(), s.row_ptr, s.col, s.w, s.nw);
-    if (rc != 0) gvc_host::die("gvc_graph_upload", rc);
-    rc = gvc_graph_layer_host(ctx, cdata(in), (int)w, mdata(out), WEIGHT_SCALE);
+    uint64_t entries = 0;
+    double t_extract = 0;
+    upload_graph(ctx, g, &entries, &t_extract);
+    const int rc = gvc_graph_layer_host(ctx, cdata(in), (int)w, mdata(out), WEIGHT_SCALE);
     if (rc != 0) gvc_host::die("gvc_graph_layer_host", rc);
 }
 
@@ -271,18 +433,17 @@ void model::predict(const matrix &in, matrix &out, const reduction_graph<Tn, Tw>
 
     predict_profile &pf = profile();
     const double t0 = now_s();
-    const csr_view s = extract_csr(ctx, g);
-    const double t1 = now_s();
-    int rc = gvc_graph_upload(ctx, n, s.row_ptr, s.col, s.w, s.nw);
-    if (rc != 0) gvc_host::die("gvc_graph_upload", rc);
+    uint64_t entries = 0;
+    double t_extract = 0;
+    upload_graph(ctx, g, &entries, &t_extract);
     const double t2 = now_s();
-    rc = gvc_forward(ctx, cdata(in), scale, mdata(out), gvc_host::mode());
+    const int rc = gvc_forward(ctx, cdata(in), scale, mdata(out), gvc_host::mode());
     if (rc != 0) gvc_host::die("gvc_forward", rc);
     const double t3 = now_s();
-    pf.calls++; pf.extract += t1 - t0; pf.upload += t2 - t1; pf.forward += t3 - t2;
+    pf.calls++; pf.extract += t_extract; pf.upload += t2 - t0 - t_extract; pf.forward += t3 - t2;
     if (pf.on)
-        std::fprintf(stderr, "gvc profile: predict n=%u nnz=%zu extract %.2f ms upload %.2f ms forward %.2f ms\n", n,
-                     (size_t)s.nnz, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2));
+        std::fprintf(stderr, "gvc profile: predict n=%u entries=%zu extract %.2f ms upload %.2f ms forward %.2f ms\n", n,
+                     (size_t)entries, 1e3 * t_extract, 1e3 * (t2 - t0 - t_extract), 1e3 * (t3 - t2));
 }
 
 // ---- text format (src/gnn_inference.cpp:92-139) --------------------------------

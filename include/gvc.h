@@ -115,6 +115,26 @@ int gvc_graph_upload_shard(gvc_ctx *ctx, uint32_t n_global, uint32_t v_begin, ui
 int gvc_graph_staging(gvc_ctx *ctx, uint32_t n_local, uint64_t nnz, uint64_t **row_ptr,
                       uint32_t **col, uint32_t **W, uint32_t **NW);
 
+/* The graph as the reduction_graph holds it (include/reduction_graph.hpp:29-33): ONE edge array with
+ * holes -- removed neighbours are rotated to the front of a list and skipped, folds append new lists
+ * at the end (:248-510) -- and a half-open range [begin, end) into it per vertex, which is exactly
+ * what begin(u)/end(u) (:692-704) expose.  Instead of compacting that into a CSR on the host and
+ * sending it (gvc_graph_upload), the caller describes it with two callbacks and libgvc streams it:
+ * worker threads (n_threads, 0 = pick) call
+ *     fill_vertices(user, first, count, begin, end, W, NW)   offsets into the span, W(u), NW(u)
+ *     fill_span(user, offset, count, dst)                    copy span[offset, offset + count) to dst
+ * for disjoint pieces, concurrently, writing straight into a small ring of pinned buffers whose
+ * earlier slots are in flight to the device meanwhile; degrees, offsets, the packed adjacency
+ * (lists in the order the span holds them), the checks of gvc_graph_upload and the degree schedule are
+ * computed on the device.  The span is [0, span_len): the caller rebases begin/end to the smallest
+ * begin.  Whole-graph contexts only (v_begin = 0, v_end = n).  This is SURVEY.md 8(f) item 2: the
+ * host neither compacts nor copies the adjacency twice, and nothing is pinned per graph. */
+typedef void (*gvc_fill_vertices_fn)(void *user, uint32_t first, uint32_t count, uint32_t *begin,
+                                     uint32_t *end, uint32_t *W, uint32_t *NW);
+typedef void (*gvc_fill_span_fn)(void *user, uint64_t offset, uint64_t count, uint32_t *dst);
+int gvc_graph_upload_stream(gvc_ctx *ctx, uint32_t n, uint64_t span_len, gvc_fill_vertices_fn fill_vertices,
+                            gvc_fill_span_fn fill_span, void *user, int n_threads);
+
 /* Same shard description with DEVICE pointers that stay owned by the caller and
  * must outlive the context's use of them (no copy; row_ptr is uint32 here, the
  * layout the kernels read).  Used by the benchmark, which builds its synthetic

@@ -1,0 +1,111 @@
+// mock_gvc.cpp -- TEST INFRASTRUCTURE ONLY: a stand-in for libgvc's entry points that does NO
+// arithmetic.  tests/test_dropin_extract_cpu.py links it with the drop-in host units
+// (gnn-mwvc_b200/host/*.cpp) so that the HOST side of gnn::model::predict -- reading a
+// reduction_graph through begin(u)/end(u)/W/NW and describing it to gvc_graph_upload_stream through
+// callbacks that several threads call concurrently -- can be checked on a machine without a GPU: the
+// mock drives the callbacks the way libgvc does (vertex chunks and span chunks handed to worker
+// threads in arbitrary order, each into its own scratch slot), rebuilds the packed CSR from what it
+// received and hands it back to the test.  Nothing here is ever part of the product.
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "gvc.h"
+
+namespace {
+std::vector<uint64_t> g_row_ptr;
+std::vector<uint32_t> g_col, g_w, g_nw;
+uint64_t g_span_len = 0;
+int g_streamed = 0;
+float g_scales[8];
+int g_n_scales = 0;
+}  // namespace
+
+struct gvc_ctx { int dummy; };
+
+extern "C" {
+const char *gvc_last_error(void) { return "mock"; }
+int gvc_ctx_create(gvc_ctx **out, int) { static gvc_ctx c; *out = &c; return 0; }
+int gvc_model_upload(gvc_ctx *, int, const int *, const int *, const int *, const float *const *, const float *const *) { return 0; }
+int gvc_model_weight_scales(gvc_ctx *, int n, const float *s) { g_n_scales = n; for (int i = 0; i < n && i < 8; ++i) g_scales[i] = s[i]; return 0; }
+
+int gvc_graph_upload_stream(gvc_ctx *, uint32_t n, uint64_t span_len, gvc_fill_vertices_fn fv, gvc_fill_span_fn fs, void *user, int) {
+    constexpr uint32_t kV = 1000;            // deliberately odd chunk sizes
+    constexpr uint64_t kS = 777;
+    std::vector<uint32_t> b(n), e(n), span(span_len);
+    g_w.assign(n, 0); g_nw.assign(n, 0);
+    const uint64_t nv = (n + kV - 1) / kV, ns = (span_len + kS - 1) / kS;
+    std::atomic<uint64_t> next{0};
+    auto work = [&](int w) {
+        std::vector<uint32_t> slot(4 * kV > kS ? 4 * kV : kS);
+        for (;;) {
+            // items are taken from both ends alternately so that span pieces arrive before vertex pieces too
+            const uint64_t k = next.fetch_add(1);
+            if (k >= nv + ns) break;
+            const uint64_t it = (k & 1) ? (nv + ns - 1 - k / 2) : k / 2;
+            if (it < nv) {
+                const uint32_t first = (uint32_t)(it * kV), cnt = std::min<uint32_t>(kV, n - first);
+                std::memset(slot.data(), 0xAB, slot.size() * 4);
+                fv(user, first, cnt, slot.data(), slot.data() + kV, slot.data() + 2 * kV, slot.data() + 3 * kV);
+                std::memcpy(b.data() + first, slot.data(), cnt * 4);
+                std::memcpy(e.data() + first, slot.data() + kV, cnt * 4);
+                std::memcpy(g_w.data() + first, slot.data() + 2 * kV, cnt * 4);
+                std::memcpy(g_nw.data() + first, slot.data() + 3 * kV, cnt * 4);
+            } else {
+                const uint64_t off = (it - nv) * kS, cnt = std::min<uint64_t>(kS, span_len - off);
+                std::memset(slot.data(), 0xCD, slot.size() * 4);
+                fs(user, off, cnt, slot.data());
+                std::memcpy(span.data() + off, slot.data(), cnt * 4);
+            }
+        }
+        (void)w;
+    };
+    std::vector<std::thread> th;
+    for (int w = 0; w < 3; ++w) th.emplace_back(work, w);
+    for (auto &t : th) t.join();
+    g_row_ptr.assign((size_t)n + 1, 0);
+    g_col.clear();
+    for (uint32_t u = 0; u < n; ++u) {
+        if (b[u] > e[u] || e[u] > span_len) return 1;
+        g_row_ptr[u] = g_col.size();
+        g_col.insert(g_col.end(), span.begin() + b[u], span.begin() + e[u]);
+    }
+    g_row_ptr[n] = g_col.size();
+    g_span_len = span_len;
+    g_streamed = 1;
+    return 0;
+}
+
+int gvc_graph_upload(gvc_ctx *, uint32_t n, const uint64_t *rp, const uint32_t *col, const uint32_t *W, const uint32_t *NW) {
+    g_row_ptr.assign(rp, rp + n + 1);
+    g_col.assign(col, col + rp[n]);
+    g_w.assign(W, W + n);
+    g_nw.assign(NW, NW + n);
+    g_span_len = rp[n];
+    g_streamed = 0;
+    return 0;
+}
+
+int gvc_graph_staging(gvc_ctx *, uint32_t, uint64_t, uint64_t **, uint32_t **, uint32_t **, uint32_t **) { return 1; }   // "no pinned buffers": callers fall back to their own
+int gvc_forward(gvc_ctx *, const float *, float, float *scores, int) { for (size_t i = 0; i + 1 < g_row_ptr.size(); ++i) scores[i] = 0.5f; return 0; }
+int gvc_graph_layer_host(gvc_ctx *, const float *, int, float *, float) { return 0; }
+int gvc_linear_host(gvc_ctx *, uint64_t, int, int, const float *, const float *, const float *, float *, int) { return 0; }
+int gvc_relu_host(gvc_ctx *, uint64_t, const float *, float *) { return 0; }
+int gvc_sigmoid_host(gvc_ctx *, uint64_t, const float *, float *, int) { return 0; }
+int gvc_sgemm_host(gvc_ctx *, int, int, uint64_t, uint64_t, uint64_t, const float *, uint64_t, const float *, uint64_t, float, float *, uint64_t) { return 0; }
+
+// what the last upload delivered: sizes first (nulls), then the arrays
+uint64_t mock_last_graph(uint64_t *row_ptr, uint32_t *col, uint32_t *w, uint32_t *nw, uint64_t *span_len, int *streamed) {
+    const size_t n = g_row_ptr.empty() ? 0 : g_row_ptr.size() - 1;
+    if (row_ptr) std::memcpy(row_ptr, g_row_ptr.data(), (n + 1) * 8);
+    if (col) std::memcpy(col, g_col.data(), g_col.size() * 4);
+    if (w) std::memcpy(w, g_w.data(), n * 4);
+    if (nw) std::memcpy(nw, g_nw.data(), n * 4);
+    if (span_len) *span_len = g_span_len;
+    if (streamed) *streamed = g_streamed;
+    return g_col.size();
+}
+int mock_last_scales(float *out) { for (int i = 0; i < g_n_scales && i < 8; ++i) out[i] = g_scales[i]; return g_n_scales; }
+}

@@ -44,6 +44,36 @@ if which == "predict":
         assert_bit_equal(got, np.asarray(vec[name + ".scores"]).reshape(-1), name)
         print("predict", name, len(w), flush=True)
     dropin.destroy(h)
+elif which == "reduced":
+    # graphs as the solver hands them to predict: the committed mutation scripts replayed on a real
+    # reduction_graph through its own mutators (holes, rotated lists, fold vertices appended at the end of
+    # the edge array, relabelled ids), predict through the drop-in -- i.e. through the streamed upload
+    # that reads begin(u)/end(u) -- against the reference's recorded scores
+    z = np.load(GOLDEN + "reduced_graphs.npz")
+    h = dropin.model(po.layers_to_text(capi.load_model_npz(GOLDEN + "mwvc_model.npz")))
+    for name in ("er3000", "er800_dense", "grid40"):
+        gh = dropin.graph_create(len(z[name + ".w0"]), z[name + ".eu"], z[name + ".ev"], z[name + ".w0"])
+        script, done = z[name + ".script"], 0
+        for rnd in range(3):
+            upto = int(z["%s.r%d.script_len" % (name, rnd)])
+            for op, u in script[done:upto]:
+                assert dropin.graph_mutate(gh, int(op), int(u)), (name, rnd, op, u)
+            done = upto
+            w = z["%s.r%d.w" % (name, rnd)]
+            assert dropin.graph_size(gh) == len(w)
+            x = w.astype(np.float32) / np.float32(200.0)
+            got = dropin.predict_on(h, gh, x, 200.0)
+            assert_bit_equal(got, z["%s.r%d.scores" % (name, rnd)], "%s round %d" % (name, rnd))
+            print("reduced", name, rnd, len(w), flush=True)
+        dropin.graph_destroy(gh)
+    # and a model whose graph layers carry different WEIGHT_SCALEs, assembled with add_layer
+    m = np.load(GOLDEN + "mixed_scales.npz")
+    layers = capi.load_model_npz(GOLDEN + "mwvc_model.npz")
+    it = iter(m["scales"])
+    hm = dropin.model_build(layers, [float(next(it)) if k == po.GRAPH else 0.0 for k, _, _ in layers])
+    gh = dropin.graph_create(len(m["w"]), m["eu"], m["ev"], m["w"])
+    assert_bit_equal(dropin.predict_on_as_is(hm, gh, m["x"]), m["scores"], "mixed scales through add_layer")
+    dropin.graph_destroy(gh)
 else:
     w = vec["er607.w"].astype(np.uint32)
     for width in (1, 16, 3):
@@ -71,3 +101,7 @@ def test_predict_through_the_reference_interface():
 
 def test_single_layer_forwards_through_the_reference_interface():
     run_child("layers")
+
+
+def test_predict_on_reduced_graphs_and_mixed_scales_through_the_reference_interface():
+    run_child("reduced")

@@ -36,6 +36,7 @@ with tempfile.TemporaryDirectory() as td:
     for name, exe, env in extra + (("reference_cpu", ref_bin, {"OPENBLAS_CORETYPE": "Prescott", "OPENBLAS_NUM_THREADS": "1"}),
                            ("reference_cpu_all_threads", ref_bin, {"OPENBLAS_CORETYPE": "Prescott"}),
                            ("b200_exact", our_bin, {"GVC_PROFILE": "1", "GVC_MODE": "exact"}),
+                           ("b200_exact_packed", our_bin, {"GVC_PROFILE": "1", "GVC_MODE": "exact", "GVC_UPLOAD": "packed"}),
                            ("b200_fast", our_bin, {"GVC_PROFILE": "1", "GVC_MODE": "fast"})):
         if only and name not in only:
             continue

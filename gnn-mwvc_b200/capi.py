@@ -220,6 +220,10 @@ class Context:
         if v_end is None:
             v_end = v_begin + nl
         self._keep = [row_ptr_i32, col_i32, W_i32, NW_i32]
+        if hasattr(row_ptr_i32, "device") and row_ptr_i32.device.type == "cuda":
+            # the tensors may still be being written on torch's streams; libgvc reads them on its own
+            import torch
+            torch.cuda.synchronize(row_ptr_i32.device)
         self._check(self.lib.gvc_graph_adopt_device(self.h, n_global, v_begin, v_end, _dptr(row_ptr_i32),
                                                     _dptr(col_i32), _dptr(W_i32), _dptr(NW_i32)))
         self.n_global, self.v_begin, self.v_end = n_global, v_begin, v_end

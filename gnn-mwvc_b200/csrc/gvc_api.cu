@@ -181,10 +181,14 @@ struct gvc_ctx {
     DevBuf<uint4> d_vrec;
     DevBuf<float> d_feat;
     // fast-mode hub chunks (gvc::HubSplit): [0] the ring vertices (width 16), [1] the stage-0 giants
-    DevBuf<uint4> d_hub_chunk[2];
-    DevBuf<uint2> d_hub_info[2];
+    // [2]: the chunks of the exact-mode "parallel exact" vertices (gvc_px.cuh), with their scratch rows and batch records
+    DevBuf<uint4> d_hub_chunk[3];
+    DevBuf<uint2> d_hub_info[3];
     DevBuf<float> d_hub_partial[2];
     DevBuf<uint32_t> d_hub_count;
+    DevBuf<float> d_px_scratch, d_px_P, d_px_D;
+    DevBuf<uint32_t> d_px_flag;
+    uint32_t px_ctr_off = 0;             // where the PX counters start inside d_sync
     gvc::Schedule sched{};
     gvc::PeerOut peers[2] = {};          // stage 0 / stage 1 outputs mirrored into the other ranks' buffers
     gvc::PartMap parts{};                // gvc_peer_owners: who owns which vertex range (n_parts == 0: not told)
@@ -396,9 +400,10 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     if (nl == 0) return 0;
     const Schedule &sc = c->sched;
     const bool exact = mode == GVC_MODE_EXACT;
-    const uint32_t n_tasks = STAGE == 0 ? (exact ? sc.n_giant1 - sc.n_ring1 : sc.n_chunks1) + (nl - sc.n_giant1 + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
-                                        : (sc.n_mid + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
-    const unsigned want = std::max<unsigned>(STAGE == 0 ? (exact ? sc.n_ring1 : 0u) : (exact ? sc.n_ring : sc.n_chunks16),
+    const uint32_t n_tasks = STAGE == 0 ? (exact ? sc.n_giant1 : sc.n_chunks1) + (nl - sc.n_giant1 + kTileVerts - 1) / kTileVerts + sc.n_feat_tiles
+                                        : (exact ? sc.n_px : 0u) + (sc.n_mid + 7) / 8 + sc.n_tiles + sc.n_feat_tiles;
+    const unsigned want = std::max<unsigned>(STAGE == 0 ? (exact ? sc.n_chunks_px : 0u)
+                                                        : (exact ? std::max(sc.n_ring - sc.n_px, sc.n_chunks_px) : sc.n_chunks16),
                                              (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta);
     // persistent kernel: never more CTAs than can be resident at once (warps wait on each other's
     // feature vectors; a CTA that is not running could never deliver its ring tasks)
@@ -415,7 +420,13 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     const uint32_t n_split = STAGE == 0 ? sc.n_giant1 : sc.n_ring;
     HubSplit hub{c->d_hub_chunk[hk].p, c->d_hub_info[hk].p, c->d_hub_partial[hk].p,
                  c->d_sync.p + kSyncCounters + sc.n_feat_tiles};
-    GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, (kSyncCounters + (size_t)sc.n_feat_tiles + (exact ? 0 : n_split)) * sizeof(uint32_t), c->stream));
+    // counters start at zero: task claims, feature tiles, then (fast) chunks done per split vertex or (exact) the
+    // claim and completion counters of the parallel exact sums
+    const size_t n_counters = exact ? (sc.n_px ? (size_t)c->px_ctr_off + 4 + 3 * (size_t)sc.n_px : kSyncCounters + (size_t)sc.n_feat_tiles)
+                                    : kSyncCounters + (size_t)sc.n_feat_tiles + n_split;
+    GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, n_counters * sizeof(uint32_t), c->stream));
+    PxArgs px{c->d_hub_chunk[2].p, c->d_hub_info[2].p, c->d_px_scratch.p, c->d_px_P.p, c->d_px_D.p, c->d_px_flag.p,
+              c->d_sync.p + c->px_ctr_off, sc.n_chunks_px, sc.n_px};
     // Cooperative launch: warps of this persistent kernel wait for feature vectors that other CTAs
     // produce, so every CTA of the grid must be resident at once.  The grid is sized for that (above);
     // the launch attribute makes the driver guarantee it even when the stream shares the GPU with other
@@ -437,10 +448,10 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     const float *a_params = c->d_stage_params[STAGE];
     const uint32_t a_vb = c->v_begin;
     if (mode == GVC_MODE_EXACT) {
-        GVC_CUDA(cudaLaunchKernelEx(&cfg, stage_kernel<STAGE, true>, a_rp, a_col, a_w, a_nw, a_order, a_vrec, sc_launch, hub, peers,
+        GVC_CUDA(cudaLaunchKernelEx(&cfg, stage_kernel<STAGE, true>, a_rp, a_col, a_w, a_nw, a_order, a_vrec, sc_launch, hub, px, peers,
                                     a_feat, a_sync, d_in, d_out, a_params, a_vb, scale));
     } else {
-        GVC_CUDA(cudaLaunchKernelEx(&cfg, stage_kernel<STAGE, false>, a_rp, a_col, a_w, a_nw, a_order, a_vrec, sc_launch, hub, peers,
+        GVC_CUDA(cudaLaunchKernelEx(&cfg, stage_kernel<STAGE, false>, a_rp, a_col, a_w, a_nw, a_order, a_vrec, sc_launch, hub, px, peers,
                                     a_feat, a_sync, d_in, d_out, a_params, a_vb, scale));
     }
     c->launches++;
@@ -522,11 +533,11 @@ int build_schedule(gvc_ctx *c) {
     uint32_t hist[kNumDegBins], start[kNumDegBins];
     GVC_CUDA(cudaMemcpyAsync(hist, c->d_bins.p, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));
-    uint32_t pos = 0, n_ring = 0, n_pre = 0, n_giant1 = 0, n_ring1 = 0;
+    uint32_t pos = 0, n_ring = 0, n_pre = 0, n_giant1 = 0, n_px = 0;
     for (int b = kNumDegBins - 1; b >= 0; --b) {          // descending degree
         if (b == degree_bin(kRingMinDeg) - 1) n_ring = pos;
         if (b == degree_bin(kGiant1MinDeg) - 1) n_giant1 = pos;
-        if (b == degree_bin(kRing1MinDeg) - 1) n_ring1 = pos;
+        if (b == degree_bin(kPxMinDeg) - 1) n_px = pos;
         if (b == degree_bin(kMidMinDeg) - 1) n_pre = pos;
         start[b] = pos;
         pos += hist[b];
@@ -536,28 +547,29 @@ int build_schedule(gvc_ctx *c) {
     sc.n_local = nl;
     sc.n_ring = n_ring;
     sc.n_giant1 = n_giant1;
-    sc.n_ring1 = std::min(n_ring1, n_giant1);
+    sc.n_px = std::min(n_px, std::min(n_ring, n_giant1));
     sc.n_mid = n_pre - n_ring;
     sc.n_tiles = (nl - n_pre + kTileVerts - 1) / kTileVerts;
     sc.n_feat_tiles = (n_pre + kTileVerts - 1) / kTileVerts;
     if ((rc = c->d_feat.reserve((size_t)n_pre * 32))) return rc;
     // counters: task claims, feature tiles, then one "chunks done" counter per split vertex
-    if ((rc = c->d_sync.reserve(kSyncCounters + (size_t)sc.n_feat_tiles + std::max(n_ring, n_giant1)))) return rc;
+    c->px_ctr_off = kSyncCounters + sc.n_feat_tiles + std::max(n_ring, n_giant1);
+    if ((rc = c->d_sync.reserve((size_t)c->px_ctr_off + 4 + 3 * (size_t)sc.n_px))) return rc;
     GVC_CUDA(cudaMemcpyAsync(c->d_bins.p, start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
     degree_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, c->Wv, nl, c->d_bins.p, c->d_order.p, c->d_vrec.p);
     GVC_CUDA(cudaGetLastError());
     c->launches++;
     // fast-mode chunk lists of the two hub classes
-    const uint32_t n_class[2] = {n_ring, n_giant1}, chunk_len[2] = {kChunk16, kChunk1};
-    uint32_t n_chunks[2] = {0, 0};
-    if ((rc = c->d_hub_count.reserve(2))) return rc;
-    GVC_CUDA(cudaMemsetAsync(c->d_hub_count.p, 0, 2 * sizeof(uint32_t), c->stream));
-    for (int k = 0; k < 2; ++k) {
+    const uint32_t n_class[3] = {n_ring, n_giant1, sc.n_px}, chunk_len[3] = {kChunk16, kChunk1, kPxChunk};
+    uint32_t n_chunks[3] = {0, 0, 0};
+    if ((rc = c->d_hub_count.reserve(3))) return rc;
+    GVC_CUDA(cudaMemsetAsync(c->d_hub_count.p, 0, 3 * sizeof(uint32_t), c->stream));
+    for (int k = 0; k < 3; ++k) {
         if (!n_class[k]) continue;
         const size_t bound = (size_t)(c->nnz / chunk_len[k]) + n_class[k];
         if ((rc = c->d_hub_chunk[k].reserve(bound))) return rc;
         if ((rc = c->d_hub_info[k].reserve(n_class[k]))) return rc;
-        if ((rc = c->d_hub_partial[k].reserve(bound * (k == 0 ? 16 : 1)))) return rc;
+        if (k < 2 && (rc = c->d_hub_partial[k].reserve(bound * (k == 0 ? 16 : 1)))) return rc;
         hub_chunks_kernel<<<std::min<unsigned>(1184, (n_class[k] + 255) / 256), 256, 0, c->stream>>>(
             c->d_vrec.p, n_class[k], chunk_len[k], c->d_hub_count.p + k, c->d_hub_info[k].p, c->d_hub_chunk[k].p,
             (uint32_t)std::min<size_t>(bound, 0xFFFFFFFFu));
@@ -568,6 +580,13 @@ int build_schedule(gvc_ctx *c) {
     GVC_CUDA(cudaStreamSynchronize(c->stream));   // `start` and `n_chunks` live on this stack frame
     sc.n_chunks16 = (uint32_t)std::min<uint64_t>(n_chunks[0], c->nnz / kChunk16 + n_ring);
     sc.n_chunks1 = (uint32_t)std::min<uint64_t>(n_chunks[1], c->nnz / kChunk1 + n_giant1);
+    sc.n_chunks_px = (uint32_t)std::min<uint64_t>(n_chunks[2], c->nnz / kPxChunk + sc.n_px);
+    if (sc.n_chunks_px) {   // scratch copy of the gathered rows and the per-batch records of the parallel exact sums
+        if ((rc = c->d_px_scratch.reserve((size_t)sc.n_chunks_px * kPxChunk * 16))) return rc;
+        if ((rc = c->d_px_P.reserve((size_t)sc.n_chunks_px * 64 * 16))) return rc;
+        if ((rc = c->d_px_D.reserve((size_t)sc.n_chunks_px * 64 * 16))) return rc;
+        if ((rc = c->d_px_flag.reserve((size_t)sc.n_chunks_px * 64))) return rc;
+    }
     // (the per-vertex peer lists read the adjacency itself: the callers build them once it has landed)
     c->have_peer_mask = false;
     return 0;
@@ -882,7 +901,9 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     c->stg_row_ptr.release(); c->stg_col.release(); c->stg_W.release(); c->stg_NW.release();
     c->d_order.release(); c->d_vrec.release(); c->d_bins.release(); c->d_sync.release(); c->d_feat.release();
     c->d_peer_mask.release();
-    for (int k = 0; k < 2; ++k) { c->d_hub_chunk[k].release(); c->d_hub_info[k].release(); c->d_hub_partial[k].release(); }
+    for (int k = 0; k < 3; ++k) { c->d_hub_chunk[k].release(); c->d_hub_info[k].release(); }
+    for (int k = 0; k < 2; ++k) c->d_hub_partial[k].release();
+    c->d_px_scratch.release(); c->d_px_P.release(); c->d_px_D.release(); c->d_px_flag.release();
     c->d_hub_count.release();
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
     c->d_ping.release(); c->d_pong.release();
@@ -1060,9 +1081,11 @@ int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_
     constexpr uint64_t kSChunk = kSlotBytes / sizeof(uint32_t);
     const uint64_t n_vchunks = ((uint64_t)n + kVChunk - 1) / kVChunk, n_schunks = (span_len + kSChunk - 1) / kSChunk;
     const uint64_t n_items = n_vchunks + n_schunks;
-    int workers = n_threads > 0 ? n_threads : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    static const int env_threads = [] { const char *e = std::getenv("GVC_UPLOAD_THREADS"); return e ? std::atoi(e) : 0; }();
+    int workers = n_threads > 0 ? n_threads : env_threads > 0 ? env_threads
+                                : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
     workers = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)workers, (n_items + 3) / 4));   // >= 4 items per thread
-    if ((rc = ensure_ring(c, std::max(2 * workers, 16), kSlotBytes))) return rc;
+    if ((rc = ensure_ring(c, std::max(2 * workers, 16) / workers * workers, kSlotBytes))) return rc;
     arena_hint(c, n, span_len);
     if ((rc = c->d_rb.reserve(n))) return rc;
     if ((rc = c->d_re.reserve(n))) return rc;
@@ -1082,20 +1105,27 @@ int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_
     // ---- host side: workers fill slots through the callbacks and send them off ------------------
     std::atomic<uint64_t> next{0};
     std::atomic<int> err{0};
+    std::atomic<uint64_t> ns_wait{0}, ns_fill{0}, ns_issue{0};        // GVC_TRACE: where the workers' time goes
+    auto now_ns = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const int slots_per_worker = c->n_slots / workers;
     auto work = [&](int w) {
         if (cudaSetDevice(c->device) != cudaSuccess) { err = 1; return; }
         int turn = 0;
         for (;;) {
             const uint64_t it = next.fetch_add(1);
             if (it >= n_items || err.load()) break;
-            const int slot = 2 * w + (turn++ & 1);
+            const int slot = slots_per_worker * w + (turn++ % slots_per_worker);
             unsigned char *host = c->ring.p + (size_t)slot * c->slot_bytes;
+            const uint64_t t0 = tr.on ? now_ns() : 0;
             if (cudaEventSynchronize(c->slot_ev[slot]) != cudaSuccess) { err = 1; break; }    // its last copy has left
+            const uint64_t t1 = tr.on ? now_ns() : 0;
+            uint64_t t2 = 0;
             cudaError_t e = cudaSuccess;
             if (it < n_vchunks) {
                 const uint32_t first = (uint32_t)(it * kVChunk), cnt = std::min<uint32_t>(kVChunk, n - first);
                 uint32_t *b = reinterpret_cast<uint32_t *>(host), *en = b + kVChunk, *w_ = en + kVChunk, *nw = w_ + kVChunk;
                 fill_vertices(user, first, cnt, b, en, w_, nw);
+                t2 = tr.on ? now_ns() : 0;
                 e = cudaMemcpyAsync(c->d_rb.p + first, b, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_re.p + first, en, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(c->own_W.p + first, w_, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
@@ -1103,10 +1133,12 @@ int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_
             } else {
                 const uint64_t off = (it - n_vchunks) * kSChunk, cnt = std::min<uint64_t>(kSChunk, span_len - off);
                 fill_span(user, off, cnt, reinterpret_cast<uint32_t *>(host));
+                t2 = tr.on ? now_ns() : 0;
                 e = cudaMemcpyAsync(c->d_span.p + off, host, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
             }
             if (e == cudaSuccess) e = cudaEventRecord(c->slot_ev[slot], c->copy_stream);
             if (e != cudaSuccess) { err = 1000 + (int)e; break; }
+            if (tr.on) { ns_wait += t1 - t0; ns_fill += t2 - t1; ns_issue += now_ns() - t2; }
         }
     };
     if (workers == 1) {
@@ -1119,6 +1151,10 @@ int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_
     }
     if (err.load()) { cudaStreamSynchronize(c->copy_stream); return fail(err.load(), "streamed upload: a copy failed"); }
     GVC_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
+    if (tr.on)
+        std::fprintf(stderr, "gvc trace: stream: %d workers, %llu items; per worker: wait for a slot %.3f ms, fill %.3f ms, issue %.3f ms\n",
+                     workers, (unsigned long long)n_items, ns_wait.load() * 1e-6 / workers, ns_fill.load() * 1e-6 / workers,
+                     ns_issue.load() * 1e-6 / workers);
     tr.tick("stream: fill + copies issued");
 
     // ---- device side: degrees -> offsets, lists -> packed CSR, checks -----------------------------

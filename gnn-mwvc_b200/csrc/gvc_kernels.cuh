@@ -93,10 +93,10 @@ constexpr uint32_t kRingMinDeg = GVC_RING_MIN_DEG;
 #ifndef GVC_GIANT1_MIN_DEG
 #define GVC_GIANT1_MIN_DEG 2048
 #endif
-#ifndef GVC_RING1_MIN_DEG
-#define GVC_RING1_MIN_DEG 16384
+#ifndef GVC_PX_MIN_DEG
+#define GVC_PX_MIN_DEG 16384
 #endif
-constexpr uint32_t kRing1MinDeg = GVC_RING1_MIN_DEG;     // stage 0, exact mode: >= a whole CTA per vertex (ring_gather1_exact)
+constexpr uint32_t kPxMinDeg = GVC_PX_MIN_DEG;           // exact mode: >= this, the sequential sum is emulated in parallel (gvc_px.cuh)
 constexpr uint32_t kGiant1MinDeg = GVC_GIANT1_MIN_DEG;   // stage 0 (w = 1): >= one warp per vertex, below one lane    // >= : ring task (whole CTA)
 constexpr uint32_t kMidMinDeg = GVC_MID_MIN_DEG;      // >= : mid task (8 vertices per warp), below: 32-vertex tiles
 constexpr int kNumDegBins = 132;
@@ -108,7 +108,8 @@ struct Schedule {
     uint32_t n_mid;        // order[n_ring, n_ring + n_mid)  mid-degree vertices, 8 per task
     uint32_t n_ring_ctas;   // CTAs [0, n_ring_ctas) share the ring tasks before joining the task queue
     uint32_t n_giant1;      // order[0, n_giant1): deg >= kGiant1MinDeg, the single-warp tasks of stage 0 (w = 1)
-    uint32_t n_ring1;       // order[0, n_ring1): deg >= kRing1MinDeg, CTA-wide in stage 0 exact mode
+    uint32_t n_px;          // order[0, n_px): deg >= kPxMinDeg, exact mode: sequential sums computed in parallel (gvc_px.cuh)
+    uint32_t n_chunks_px;   // their 4096-entry chunks
     uint32_t n_tiles;       // 32-vertex tiles over order[n_ring + n_mid, n_local)
     uint32_t n_feat_tiles;  // 32-vertex feature tiles over order[0, n_ring + n_mid)
     uint32_t n_chunks16;    // fast mode: chunks the ring vertices are cut into (HubSplit), width 16
@@ -813,93 +814,6 @@ __device__ __noinline__ float coop_gather1(float *__restrict__ S /* >= 256 float
     return acc;
 }
 
-// CTA-wide task, width 1, exact mode (the few vertices of degree >= kRing1MinDeg in stage 0).
-// As a single-warp task (coop_gather1) the chain warp also fetches, and shares its scheduler with
-// warps running dense tiles: ~35 % of its time goes into the fetch code, and on a busy SM it falls
-// from 3.1 to ~5 ns per neighbour -- the longest of these chains is the critical path of stage 0.
-// Here warp 0 does nothing but the chain (the sum stays in its registers), warps 1..7 fetch:
-// loader i gathers blocks i, i+7, ... (256 neighbours each) into its own tile buffer, one block
-// parked, one in registers, ids one further ahead.  full[i]/empty[i] named barriers as a
-// producer/consumer pair per buffer; the chain warp syncs on the next buffer before it sums the
-// current one.  Returns the sum in warp 0 (other warps: 0).
-constexpr int kRing1Loaders = kWarpsPerCta - 1;
-static_assert(kRing1Loaders >= 2 && 2 * kRing1Loaders + 1 <= 16, "two named barriers per loader, ids 1..15");
-
-__device__ __noinline__ float ring_gather1_exact(float *__restrict__ warp_mem, const uint32_t *__restrict__ col,
-                                                 const float *__restrict__ x, uint32_t beg, uint32_t end,
-                                                 int warp, int lane) {
-    constexpr int L = kRing1Loaders;
-    constexpr int kFull = 1, kEmpty = 1 + L;
-    const uint32_t nb = (end - beg + 255) / 256;
-    if (nb == 0) return 0.0f;
-    if (warp == 0) {
-        float acc = 0.0f;
-        named_bar_sync(kFull, 64);
-#pragma unroll 1
-        for (uint32_t b = 0; b < nb; ++b) {
-            const int i = (int)(b % L);
-            const float *S = warp_mem + (1 + i) * kWarpSmemFloats;
-            if (b + 1 < nb) named_bar_sync(kFull + (int)((b + 1) % L), 64);     // normally full long since
-            const int cnt = (int)min(256u, end - (beg + 256 * b));
-            const float4 *s4 = reinterpret_cast<const float4 *>(S);
-            int j = 0;
-            if (cnt == 256) {
-                // the next 16 values are loaded while the current 16 are added (a rolled loop with a
-                // window of 32 values ahead was measured slower: 3.25 vs 2.85 ns per neighbour)
-                float4 a = s4[0], bq = s4[1], c = s4[2], d = s4[3];
-#pragma unroll 4
-                for (; j < 256; j += 16) {
-                    const int n4 = (j + 16 < 256) ? (j + 16) / 4 : 0;
-                    const float4 na = s4[n4], nb4 = s4[n4 + 1], nc = s4[n4 + 2], nd = s4[n4 + 3];
-                    acc = __fadd_rn(acc, a.x); acc = __fadd_rn(acc, a.y); acc = __fadd_rn(acc, a.z); acc = __fadd_rn(acc, a.w);
-                    acc = __fadd_rn(acc, bq.x); acc = __fadd_rn(acc, bq.y); acc = __fadd_rn(acc, bq.z); acc = __fadd_rn(acc, bq.w);
-                    acc = __fadd_rn(acc, c.x); acc = __fadd_rn(acc, c.y); acc = __fadd_rn(acc, c.z); acc = __fadd_rn(acc, c.w);
-                    acc = __fadd_rn(acc, d.x); acc = __fadd_rn(acc, d.y); acc = __fadd_rn(acc, d.z); acc = __fadd_rn(acc, d.w);
-                    a = na; bq = nb4; c = nc; d = nd;
-                }
-            }
-            for (; j < cnt; ++j) acc = __fadd_rn(acc, S[j]);
-            __syncwarp();
-            if (b + L < nb) named_bar_arrive(kEmpty + i, 64);  // loader i has another block for this buffer
-        }
-        return acc;
-    }
-    // ---- loader i = warp - 1 -----------------------------------------------------------------
-    const int i = warp - 1;
-    float *S = warp_mem + warp * kWarpSmemFloats;
-    uint32_t id[8];
-    float v[8], vn[8];
-    auto ld_ids = [&](uint32_t blk) {
-        const uint32_t e0 = beg + 256 * blk, lim = blk < nb ? end : 0u;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; id[t] = (e < lim) ? ld_id(col + e) : 0u; }
-    };
-    auto ld_x = [&](float (&val)[8], uint32_t blk) {
-        const uint32_t e0 = beg + 256 * blk, lim = blk < nb ? end : 0u;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) { const uint32_t e = e0 + 32 * t + lane; val[t] = (e < lim) ? __ldg(x + id[t]) : 0.0f; }
-    };
-    uint32_t b = i;
-    ld_ids(b);
-    ld_x(v, b);
-    ld_ids(b + L);
-    bool first = true;
-#pragma unroll 1
-    for (; b < nb; b += L) {
-        ld_x(vn, b + L);                                       // next block's values in flight
-        ld_ids(b + 2 * L);
-        if (!first) named_bar_sync(kEmpty + i, 64);            // the chain has read the previous contents
-        first = false;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) S[32 * t + lane] = v[t];
-        __threadfence_block();
-        named_bar_arrive(kFull + i, 64);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = vn[t];
-    }
-    return 0.0f;
-}
-
 // fast mode: every lane sums its own elements, one shuffle reduction at the end; the values of
 // the next block and the ids of the one after are in flight while a block is added up
 __device__ __noinline__ float coop_gather1_fast(const uint32_t *__restrict__ col, const float *__restrict__ x,
@@ -935,6 +849,10 @@ __device__ __noinline__ float coop_gather1_fast(const uint32_t *__restrict__ col
     for (int m = 1; m < 32; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
     return acc;
 }
+
+}  // namespace gvc
+#include "gvc_px.cuh"
+namespace gvc {
 
 // ---- feature vectors of ring/mid vertices: feat[pos * 32 + k] -------------------------------------
 // width 16: lanes 0-15 hold agg[c], lanes 16-31 supply self[c] with the :38-40 quirk
@@ -983,7 +901,7 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
              const uint32_t *__restrict__ Wv, const uint32_t *__restrict__ NWv,
              const uint32_t *__restrict__ order, const uint4 *__restrict__ vrec, const Schedule sc,
-             const HubSplit hub, const PeerOut peers_arg, float *__restrict__ feat,
+             const HubSplit hub, const PxArgs px, const PeerOut peers_arg, float *__restrict__ feat,
              uint32_t *__restrict__ sync, const float *__restrict__ in, float *__restrict__ out,
              const float *__restrict__ params, uint32_t v_begin, float scale) {
     constexpr StageDims D = stage_dims(STAGE);
@@ -1006,33 +924,23 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
 
     // ---- ring tasks (width 16 only): the whole CTA, largest vertices first --------------------
     // (stage 0 runs its giants below 16384 neighbours as single-warp tasks of the queue instead)
-    if constexpr (STAGE == 0 && EXACT) {
-        // stage 0, exact mode: the few vertices whose sequential sum is long enough to be the
-        // critical path of the stage get a whole CTA (ring_gather1_exact), largest first
-        uint32_t *claim = reinterpret_cast<uint32_t *>(ring_acc) + 16;
-#pragma unroll 1
-        while (blockIdx.x < sc.n_ring_ctas && sc.n_ring1) {
-            if (threadIdx.x == 0) *claim = atomicAdd(sync + 3, 1u);
-            __syncthreads();
-            const uint32_t g = *claim;
-            if (g >= sc.n_ring1) break;
-            const uint32_t ul = __ldg(order + g);
-            const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-            const float acc = ring_gather1_exact(warp_mem, col, in, beg, end, warp, lane);
-            if (warp == 0) {
-                put_features1(feat, g, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
-                publish_feature(ready, g, lane);
-            }
-            __syncthreads();
-        }
+    // ---- exact mode: the vertices of degree >= kPxMinDeg ------------------------------------------
+    // Their sequential sums are emulated in parallel (gvc_px.cuh): the chunks of their lists are gathered
+    // and quantised here by whole CTAs (phases A and B); the in-order walk over the batches (phase C)
+    // is a single-warp task at the very front of the queue below, so that it starts at once on the
+    // CTAs that do not take part here and overlaps everything else the stage has to do.
+    if constexpr (EXACT) {
+        if (blockIdx.x < sc.n_ring_ctas && sc.n_px)
+            px_phases_ab<STAGE == 0 ? 1 : 16>(px, col, in, reinterpret_cast<uint32_t *>(ring_acc) + 16,
+                                              reinterpret_cast<double *>(warp_mem), warp, lane);
     }
     if constexpr (STAGE != 0) {
         // claimed one at a time, largest first: a CTA that drew a huge vertex takes fewer of them
         uint32_t *claim = reinterpret_cast<uint32_t *>(ring_acc) + 16;
         if constexpr (EXACT) {
 #pragma unroll 1
-            while (blockIdx.x < sc.n_ring_ctas && sc.n_ring) {
-                if (threadIdx.x == 0) *claim = atomicAdd(sync + 3, 1u);
+            while (blockIdx.x < sc.n_ring_ctas && sc.n_ring > sc.n_px) {
+                if (threadIdx.x == 0) *claim = sc.n_px + atomicAdd(sync + 3, 1u);     // [0, n_px) go the parallel way
                 __syncthreads();
                 const uint32_t g = *claim;
                 if (g >= sc.n_ring) break;
@@ -1113,7 +1021,8 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     // their chunks); everything else is a 32-vertex tile.
     // stages 1/2: front = mid tasks (8 vertices each); tiles hold the vertices of degree < 64.
     const uint32_t n_pre = STAGE == 0 ? sc.n_giant1 : sc.n_ring + sc.n_mid;   // positions that go through feature tiles
-    const uint32_t n_front = STAGE == 0 ? (EXACT ? sc.n_giant1 - sc.n_ring1 : sc.n_chunks1) : (sc.n_mid + 7) / 8;
+    const uint32_t n_walk = EXACT ? sc.n_px : 0u;           // front of the front: the phase-C walks of the largest vertices
+    const uint32_t n_front = STAGE == 0 ? (EXACT ? sc.n_giant1 : sc.n_chunks1) : n_walk + (sc.n_mid + 7) / 8;
     const uint32_t n_tiles = (sc.n_local - n_pre + kTileVerts - 1) / kTileVerts;
     const uint32_t n_heavy = n_front + n_tiles;             // dealt alternately from both ends
     const uint32_t n_tasks = n_heavy + (n_pre + kTileVerts - 1) / kTileVerts;
@@ -1137,10 +1046,10 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
         if (k < n_heavy) {
             if (g < n_front) {
                 if constexpr (STAGE == 0 && EXACT) {
-                    const uint32_t pos = sc.n_ring1 + g;               // the largest went through the ring phase
+                    const uint32_t pos = g;
                     const uint32_t ul = __ldg(order + pos);
                     const uint32_t beg = __ldg(row_ptr + ul), end = __ldg(row_ptr + ul + 1);
-                    const float acc = coop_gather1(T, col, in, beg, end, lane);
+                    const float acc = g < n_walk ? px_walk1(px, g, end - beg, lane) : coop_gather1(T, col, in, beg, end, lane);
                     put_features1(feat, pos, acc, in, ul, end - beg, Wv, NWv, v_begin, scale, lane);
                     publish_feature(ready, pos, lane);
                 } else if constexpr (STAGE == 0) {
@@ -1171,8 +1080,14 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
                         put_features1(feat, pos, acc, in, ul, deg, Wv, NWv, v_begin, scale, lane);
                         publish_feature(ready, pos, lane);
                     }
+                } else if (EXACT && g < n_walk) {
+                    const uint32_t ul = __ldg(order + g);
+                    const uint32_t deg = __ldg(row_ptr + ul + 1) - __ldg(row_ptr + ul);
+                    const float acc = px_walk16(px, g, deg, lane);
+                    put_features16(feat, g, acc, in, ul, deg, Wv, NWv, v_begin, scale, lane);
+                    publish_feature(ready, g, lane);
                 } else {
-                    const uint32_t pos0 = sc.n_ring + 8 * g;
+                    const uint32_t pos0 = sc.n_ring + 8 * (g - n_walk);
                     gather16_mid_task(feat, ready, order, pos0, (int)min(8u, n_pre - pos0), row_ptr, col, Wv, NWv,
                                       reinterpret_cast<const float4 *>(in), v_begin, scale, lane);
                 }

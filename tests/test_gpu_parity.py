@@ -467,6 +467,7 @@ def test_full_size_grid_properties(ctx):
     nwu = (g.row_ptr[1:] - g.row_ptr[:-1]).to(torch.int32) * 7
     ctx.graph_adopt(g.row_ptr.to(torch.int32).contiguous(), g.col, wu, nwu)
     xu = (wu.to(torch.float32) / s).contiguous()
+    torch.cuda.synchronize()                                   # xu is written on torch's stream, read on libgvc's
     ctx.forward_device(xu, s, a, pkg.MODE_EXACT)
     ctx.sync()
     inner = a.view(side, side)[3:-3, 3:-3]
@@ -672,3 +673,55 @@ def test_peer_lists_built_after_the_adjacency_landed(ctx, model_layers):
     arrived = ~torch.isnan(other).any(1).cpu().numpy()
     assert np.array_equal(arrived, must), (arrived.sum(), must.sum())
     c.close()
+
+
+def _star(deg, extra=0, seed=3):
+    """vertex 0 with `deg` neighbours (+ `extra` random edges among the leaves)"""
+    n = deg + 1
+    eu = [torch.zeros(deg, dtype=torch.int64)]
+    ev = [torch.arange(1, deg + 1, dtype=torch.int64)]
+    if extra:
+        r = torch.from_numpy(np.random.default_rng(seed).integers(1, n, size=(extra, 2)))
+        eu.append(r[:, 0]); ev.append(r[:, 1])
+    a, b = graphs._canonical_edges(torch.cat(eu), torch.cat(ev), n)
+    return graphs.graph_from_edges(n, a, b, graphs.random_weights(n, seed), name=f"star{deg}")
+
+
+@pytest.mark.parametrize("deg", [16_384, 40_000, 262_144])
+def test_parallel_exact_hub_sums(ctx, oracle, oracle_model, deg):
+    """Vertices of degree >= 16 384 take the parallel emulation of the sequential sum (gvc_px.cuh):
+    bit-equal to the oracle's element-wise chain, shuffled adjacency, all three stages."""
+    g = _star(deg, extra=3 * deg)
+    rp, col, W, NW, x, s = inputs_of(g)
+    col = col.copy()
+    np.random.default_rng(deg).shuffle(col[int(rp[0]):int(rp[1])])
+    want = oracle.predict(oracle_model, rp, col, W, NW, x, s)[:, 0]
+    ctx.graph_upload(rp, col, W, NW)
+    assert_bit_equal(ctx.forward(x, s, pkg.MODE_EXACT), want, g.name)
+    assert_rel_close(ctx.forward(x, s, pkg.MODE_FAST), want, FAST_RTOL, g.name + " fast")
+
+
+def test_parallel_exact_hub_sums_survive_hostile_inputs(ctx, oracle, oracle_model):
+    """predict must use the `in` it is given: negative, zero, huge, denormal and NaN inputs under a hub
+    (stage 0 sees them raw).  The fast way's preconditions fail and the batches fall back to the chain."""
+    g = _star(50_000, extra=20_000)
+    rp, col, W, NW, _, s = inputs_of(g)
+    rng = np.random.default_rng(4)
+    base = rng.random(g.n).astype(np.float32)
+    variants = {
+        "negatives": (rng.standard_normal(g.n)).astype(np.float32),
+        "zeros and ties": (rng.integers(0, 4, g.n) * 0.25).astype(np.float32),
+        "outliers": np.where(rng.random(g.n) < 0.001, 3e7, base).astype(np.float32),
+        "denormals": (base * 1e-39).astype(np.float32),
+        "wide": np.exp(rng.uniform(-30, 10, g.n)).astype(np.float32),
+    }
+    ctx.graph_upload(rp, col, W, NW)
+    for name, x in variants.items():
+        want = oracle.predict(oracle_model, rp, col, W, NW, x, s)[:, 0]
+        assert_bit_equal(ctx.forward(x, s, pkg.MODE_EXACT), want, name)
+    x = base.copy(); x[col[int(rp[0]) + 777]] = np.nan          # one NaN among the hub's neighbours
+    want = oracle.predict(oracle_model, rp, col, W, NW, x, s)[:, 0]
+    got = ctx.forward(x, s, pkg.MODE_EXACT)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert_bit_equal(got[ok], want[ok], "NaN under the hub")

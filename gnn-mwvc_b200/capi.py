@@ -11,8 +11,10 @@ from pathlib import Path
 
 import numpy as np
 
+import os
+
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libgvc.so"
+LIB_PATH = Path(os.environ["GVC_LIB"]) if os.environ.get("GVC_LIB") else PKG_DIR / "libgvc.so"     # GVC_LIB: an experimental build
 
 LINEAR, GRAPH, RELU, SIGMOID = 0, 1, 2, 3
 MODE_EXACT, MODE_FAST = 0, 1
@@ -46,6 +48,9 @@ SIGNATURES = {
     "gvc_peer_owners": (C.c_int, [C.c_void_p, C.c_int, _u32p, _i32p]),
     "gvc_forward": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, C.c_int]),
     "gvc_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]),
+    "gvc_forward_keys": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, _f32p, C.POINTER(C.c_ubyte), C.c_int]),
+    "gvc_last_keys": (C.c_int, [C.c_void_p, _f32p, C.POINTER(C.c_ubyte)]),
+    "gvc_forward_device_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "gvc_stage_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int]),
     "gvc_graph_layer_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float]),
     "gvc_linear_layer_device": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
@@ -62,6 +67,7 @@ SIGNATURES = {
     "gvc_sync": (C.c_int, [C.c_void_p]),
     "gvc_launch_count": (C.c_uint64, [C.c_void_p]),
     "gvc_debug_h": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "gvc_debug_px": (C.c_int, [C.c_void_p, _u32p]),
 }
 
 
@@ -278,6 +284,18 @@ class Context:
         self._check(self.lib.gvc_forward(self.h, _ptr(x, _f32p), float(weight_scale), _ptr(out, _f32p), mode))
         return out
 
+    def forward_keys(self, x, weight_scale: float, mode: int = MODE_EXACT):
+        """(scores, keys = min(s, 1 - s), side = s > 0.5): the inputs of the caller's selection order."""
+        x = _np(x, np.float32).ravel()
+        if x.size != self.n_global:
+            raise GvcError(f"x has {x.size} entries, graph has {self.n_global} vertices")
+        out = np.empty(self.n_global, np.float32)
+        keys = np.empty(self.n_global, np.float32)
+        side = np.empty(self.n_global, np.uint8)
+        self._check(self.lib.gvc_forward_keys(self.h, _ptr(x, _f32p), float(weight_scale), _ptr(out, _f32p), _ptr(keys, _f32p),
+                                              side.ctypes.data_as(C.POINTER(C.c_ubyte)), mode))
+        return out, keys, side
+
     def forward_device(self, d_x, weight_scale: float, d_scores, mode: int = MODE_EXACT):
         self._check(self.lib.gvc_forward_device(self.h, _dptr(d_x), float(weight_scale), _dptr(d_scores), mode))
 
@@ -354,6 +372,13 @@ class Context:
 
     def sync(self):
         self._check(self.lib.gvc_sync(self.h))
+
+    def px_stats(self):
+        """{hubs, chunks, slow batches} of the parallel exact hub sums in the last stage launched."""
+        out = np.zeros(8, np.uint32)
+        self._check(self.lib.gvc_debug_px(self.h, _ptr(out, _u32p)))
+        return {"hubs": int(out[0]), "chunks": int(out[1]), "slow_batches": int(out[3]),
+                "walk_wait_kcycles": int(out[5]), "walk_kcycles": int(out[6]), "quantiser_dirty": int(out[7])}
 
     @property
     def launches(self) -> int:

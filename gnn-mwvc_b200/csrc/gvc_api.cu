@@ -186,7 +186,7 @@ struct gvc_ctx {
     DevBuf<uint2> d_hub_info[3];
     DevBuf<float> d_hub_partial[2];
     DevBuf<uint32_t> d_hub_count;
-    DevBuf<float> d_px_scratch, d_px_P, d_px_D;
+    DevBuf<float> d_px_scratch, d_px_S, d_px_T, d_px_rec;
     DevBuf<uint32_t> d_px_flag;
     uint32_t px_ctr_off = 0;             // where the PX counters start inside d_sync
     gvc::Schedule sched{};
@@ -200,6 +200,11 @@ struct gvc_ctx {
 
     // activations
     DevBuf<float> d_x, d_h1, d_h2, d_scores, d_ping, d_pong;
+    DevBuf<float> d_keys;                // selection keys of the last forward (gvc_forward_keys)
+    DevBuf<uint8_t> d_side;
+    uint32_t keys_valid_n = 0;           // d_keys/d_side hold the keys of the last gvc_forward for this many vertices
+    float *keys_out = nullptr;           // where stage 2 of the NEXT launch writes them (null: not wanted)
+    uint8_t *side_out = nullptr;
     PinBuf<float> pin_x, pin_scores;
 
     uint32_t n_local() const { return v_end - v_begin; }
@@ -415,6 +420,8 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     PeerOut peers{};
     if (STAGE < 2) peers = c->peers[STAGE];
     peers.n_live = c->n_live;
+    peers.keys = STAGE == 2 ? c->keys_out : nullptr;
+    peers.side = STAGE == 2 ? c->side_out : nullptr;
     peers.mask = c->have_peer_mask ? c->d_peer_mask.p - c->v_begin : nullptr;
     const int hk = STAGE == 0 ? 1 : 0;
     const uint32_t n_split = STAGE == 0 ? sc.n_giant1 : sc.n_ring;
@@ -422,10 +429,10 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
                  c->d_sync.p + kSyncCounters + sc.n_feat_tiles};
     // counters start at zero: task claims, feature tiles, then (fast) chunks done per split vertex or (exact) the
     // claim and completion counters of the parallel exact sums
-    const size_t n_counters = exact ? (sc.n_px ? (size_t)c->px_ctr_off + 4 + 3 * (size_t)sc.n_px : kSyncCounters + (size_t)sc.n_feat_tiles)
+    const size_t n_counters = exact ? (sc.n_px ? (size_t)c->px_ctr_off + 8 + 3 * (size_t)sc.n_px : kSyncCounters + (size_t)sc.n_feat_tiles)
                                     : kSyncCounters + (size_t)sc.n_feat_tiles + n_split;
     GVC_CUDA(cudaMemsetAsync(c->d_sync.p, 0, n_counters * sizeof(uint32_t), c->stream));
-    PxArgs px{c->d_hub_chunk[2].p, c->d_hub_info[2].p, c->d_px_scratch.p, c->d_px_P.p, c->d_px_D.p, c->d_px_flag.p,
+    PxArgs px{c->d_hub_chunk[2].p, c->d_hub_info[2].p, c->d_px_scratch.p, c->d_px_S.p, c->d_px_T.p, c->d_px_rec.p, c->d_px_flag.p,
               c->d_sync.p + c->px_ctr_off, sc.n_chunks_px, sc.n_px};
     // Cooperative launch: warps of this persistent kernel wait for feature vectors that other CTAs
     // produce, so every CTA of the grid must be resident at once.  The grid is sized for that (above);
@@ -554,7 +561,7 @@ int build_schedule(gvc_ctx *c) {
     if ((rc = c->d_feat.reserve((size_t)n_pre * 32))) return rc;
     // counters: task claims, feature tiles, then one "chunks done" counter per split vertex
     c->px_ctr_off = kSyncCounters + sc.n_feat_tiles + std::max(n_ring, n_giant1);
-    if ((rc = c->d_sync.reserve((size_t)c->px_ctr_off + 4 + 3 * (size_t)sc.n_px))) return rc;
+    if ((rc = c->d_sync.reserve((size_t)c->px_ctr_off + 8 + 3 * (size_t)sc.n_px))) return rc;
     GVC_CUDA(cudaMemcpyAsync(c->d_bins.p, start, sizeof(start), cudaMemcpyHostToDevice, c->stream));
     degree_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->row_ptr, c->Wv, nl, c->d_bins.p, c->d_order.p, c->d_vrec.p);
     GVC_CUDA(cudaGetLastError());
@@ -583,8 +590,9 @@ int build_schedule(gvc_ctx *c) {
     sc.n_chunks_px = (uint32_t)std::min<uint64_t>(n_chunks[2], c->nnz / kPxChunk + sc.n_px);
     if (sc.n_chunks_px) {   // scratch copy of the gathered rows and the per-batch records of the parallel exact sums
         if ((rc = c->d_px_scratch.reserve((size_t)sc.n_chunks_px * kPxChunk * 16))) return rc;
-        if ((rc = c->d_px_P.reserve((size_t)sc.n_chunks_px * 64 * 16))) return rc;
-        if ((rc = c->d_px_D.reserve((size_t)sc.n_chunks_px * 64 * 16))) return rc;
+        if ((rc = c->d_px_S.reserve((size_t)sc.n_chunks_px * 64 * 16))) return rc;
+        if ((rc = c->d_px_T.reserve((size_t)sc.n_chunks_px * 16))) return rc;
+        if ((rc = c->d_px_rec.reserve((size_t)sc.n_chunks_px * 64 * 32))) return rc;
         if ((rc = c->d_px_flag.reserve((size_t)sc.n_chunks_px * 64))) return rc;
     }
     // (the per-vertex peer lists read the adjacency itself: the callers build them once it has landed)
@@ -835,6 +843,7 @@ int set_graph_views(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_
     c->n_global = n_global; c->v_begin = v_begin; c->v_end = v_end; c->nnz = nnz;
     c->row_ptr = rp; c->col = col; c->Wv = W; c->NWv = NW;
     c->have_graph = true;
+    c->keys_valid_n = 0;
     c->tail_override = -1;
     int rc;
     if ((rc = ensure_activations(c))) return rc;
@@ -903,10 +912,10 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     c->d_peer_mask.release();
     for (int k = 0; k < 3; ++k) { c->d_hub_chunk[k].release(); c->d_hub_info[k].release(); }
     for (int k = 0; k < 2; ++k) c->d_hub_partial[k].release();
-    c->d_px_scratch.release(); c->d_px_P.release(); c->d_px_D.release(); c->d_px_flag.release();
+    c->d_px_scratch.release(); c->d_px_S.release(); c->d_px_T.release(); c->d_px_rec.release(); c->d_px_flag.release();
     c->d_hub_count.release();
     c->d_x.release(); c->d_h1.release(); c->d_h2.release(); c->d_scores.release();
-    c->d_ping.release(); c->d_pong.release();
+    c->d_ping.release(); c->d_pong.release(); c->d_keys.release(); c->d_side.release();
     c->pin_x.release(); c->pin_scores.release();
     c->arena.release_all();
     tl_arena = nullptr;
@@ -1416,7 +1425,17 @@ int gvc_forward(gvc_ctx *c, const float *x, float scale, float *scores, int mode
         GVC_CUDA(cudaEventRecord(c->slot_ev[slot], c->stream));
     }
     tr.tick("forward: x up");
-    if ((rc = gvc_forward_device(c, c->d_x.p, scale, c->d_scores.p, mode))) return rc;
+    // the selection keys are a by-product of stage 2 (5 bytes per vertex): kept on the device for gvc_last_keys
+    const bool own_keys = c->fused && !c->keys_out;
+    if (own_keys) {
+        if ((rc = c->d_keys.reserve(n))) return rc;
+        if ((rc = c->d_side.reserve(n))) return rc;
+        c->keys_out = c->d_keys.p;
+        c->side_out = c->d_side.p;
+    }
+    rc = gvc_forward_device(c, c->d_x.p, scale, c->d_scores.p, mode);
+    if (own_keys) { c->keys_out = nullptr; c->side_out = nullptr; c->keys_valid_n = rc ? 0 : n; }
+    if (rc) return rc;
     for (size_t k0 = 0; k0 < chunks; k0 += c->n_slots) {           // as many chunks as there are slots per round
         const size_t k1 = std::min(chunks, k0 + (size_t)c->n_slots);
         for (size_t k = k0; k < k1; ++k) {
@@ -1434,6 +1453,41 @@ int gvc_forward(gvc_ctx *c, const float *x, float scale, float *scores, int mode
         }
     }
     tr.tick("forward: kernels + scores down");
+    return 0;
+}
+
+int gvc_forward_device_keys(gvc_ctx *c, const float *d_x, float scale, float *d_scores, float *d_keys,
+                            unsigned char *d_side, int mode) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!c->fused) return fail(GVC_ERR_UNSUPPORTED, "selection keys come out of the fused stage-2 kernel (GNN_VC architecture only)");
+    if (c->n_global && (!d_keys || !d_side)) return fail(GVC_ERR_ARG, "null buffer");
+    c->keys_out = d_keys;
+    c->side_out = d_side;
+    rc = gvc_forward_device(c, d_x, scale, d_scores, mode);
+    c->keys_out = nullptr;
+    c->side_out = nullptr;
+    return rc;
+}
+
+int gvc_forward_keys(gvc_ctx *c, const float *x, float scale, float *scores, float *keys, unsigned char *side, int mode) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!c->fused) return fail(GVC_ERR_UNSUPPORTED, "selection keys come out of the fused stage-2 kernel (GNN_VC architecture only)");
+    if ((rc = gvc_forward(c, x, scale, scores, mode))) return rc;
+    return gvc_last_keys(c, keys, side);
+}
+
+int gvc_last_keys(gvc_ctx *c, float *keys, unsigned char *side) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!c->have_graph || c->keys_valid_n != c->n_global) return fail(GVC_ERR_STATE, "no forward of the current graph has left selection keys");
+    if (!c->n_global) return 0;
+    if (!keys || !side) return fail(GVC_ERR_ARG, "null buffer");
+    if ((rc = use_device(c))) return rc;
+    GVC_CUDA(cudaMemcpyAsync(keys, c->d_keys.p, (size_t)c->n_global * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaMemcpyAsync(side, c->d_side.p, (size_t)c->n_global, cudaMemcpyDeviceToHost, c->stream));
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -1618,6 +1672,19 @@ int gvc_sync(gvc_ctx *c) {
 }
 
 uint64_t gvc_launch_count(const gvc_ctx *c) { return c ? c->launches : 0; }
+
+int gvc_debug_px(gvc_ctx *c, uint32_t *out4) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if (!out4) return fail(GVC_ERR_ARG, "null buffer");
+    out4[0] = c->sched.n_px; out4[1] = c->sched.n_chunks_px;
+    for (int i = 2; i < 8; ++i) out4[i] = 0;
+    if (!c->have_graph || !c->sched.n_px) return 0;
+    if ((rc = use_device(c))) return rc;
+    GVC_CUDA(cudaStreamSynchronize(c->stream));
+    GVC_CUDA(cudaMemcpy(out4 + 2, c->d_sync.p + c->px_ctr_off + 2, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 const float *gvc_debug_h(const gvc_ctx *c, int which) {
     if (!c) return nullptr;

@@ -73,7 +73,7 @@ constexpr int kTileVerts = 32;            // vertices per warp tile
 constexpr int kTileStride = 36;           // floats per k-row of a tile (32 + 4 pad, keeps float4 alignment)
 constexpr int kTileRows = 32;             // widest activation
 constexpr int kTileFloats = kTileRows * kTileStride;
-constexpr int kWarpSmemFloats = kTileFloats + 32;   // tile + vid[32]
+constexpr int kWarpSmemFloats = kTileFloats + 64;   // tile + vid[32] + 32 (gvc_px.cuh parks four batch records behind a staged batch)
 constexpr int kSyncCounters = 4;          // sync[0..2] task claims, sync[3] ring claims; then the feature-tile counters
 
 #ifndef GVC_MID_SETS
@@ -141,7 +141,19 @@ struct PeerOut {
                             // neighbour of the vertex and therefore reads its row; null = every peer gets every row
     int n;                  // 0: single GPU, or rows exchanged by a collective instead
     uint32_t n_live;        // positions of `order` below this hold vertices with neighbours
+    // stage 2 only: what the caller's selection order is computed from
+    // (src/GNN_VC.cpp:194-206), written beside the scores; null = not wanted
+    float *keys;            // [n_local] min(out, 1 - out)
+    uint8_t *side;          // [n_local] out > 0.5
 };
+// std::min(s, 1.0f - s) and s > 0.5f exactly as the caller's comparator evaluates them
+__device__ __forceinline__ void store_selection_key(const PeerOut &po, uint32_t i, float s) {
+    if (po.keys) {
+        const float r = __fsub_rn(1.0f, s);
+        po.keys[i] = (r < s) ? r : s;
+        po.side[i] = s > 0.5f ? 1 : 0;
+    }
+}
 
 struct HubSplit {
     const uint4 *chunk;
@@ -328,7 +340,11 @@ __device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const u
             od = mac<EXACT>(T[(k + 1) * kTileStride + lane], Wc[k + 1], od);
         }
         const float s = __fadd_rn(__fadd_rn(ev, od), bc[0]);
-        if (lane < count) out[vid[lane] - v_begin] = sigmoid_ref<EXACT>(s);
+        if (lane < count) {
+            const float sg = sigmoid_ref<EXACT>(s);
+            out[vid[lane] - v_begin] = sg;
+            store_selection_key(peers, vid[lane] - v_begin, sg);
+        }
     }
     __syncwarp();
 }
@@ -909,9 +925,9 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     float *P = smem;                                             // packed parameters
     constexpr int kParamFloats = (D.floats() + 3) / 4 * 4;
     float *ring_acc = smem + kParamFloats;                       // 16 sums, the CTA's ring claim [16], a chunk record [20..23],
-    PeerOut &peers = *reinterpret_cast<PeerOut *>(ring_acc + 24);   // the peer table [24..43] (shared memory: passed by reference)
-    static_assert(sizeof(PeerOut) <= 80, "PeerOut is laid out in 20 floats of shared memory");
-    float *warp_mem = ring_acc + 44;
+    PeerOut &peers = *reinterpret_cast<PeerOut *>(ring_acc + 24);   // the peer table [24..47] (shared memory: passed by reference)
+    static_assert(sizeof(PeerOut) <= 96, "PeerOut is laid out in 24 floats of shared memory");
+    float *warp_mem = ring_acc + 48;
 
     for (int i = threadIdx.x; i < D.floats(); i += kCtaThreads) P[i] = __ldg(params + i);
     if (threadIdx.x == 0) peers = peers_arg;
@@ -931,8 +947,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     // CTAs that do not take part here and overlaps everything else the stage has to do.
     if constexpr (EXACT) {
         if (blockIdx.x < sc.n_ring_ctas && sc.n_px)
-            px_phases_ab<STAGE == 0 ? 1 : 16>(px, col, in, reinterpret_cast<uint32_t *>(ring_acc) + 16,
-                                              reinterpret_cast<double *>(warp_mem), warp, lane);
+            px_phases_ab<STAGE == 0 ? 1 : 16>(px, col, in, reinterpret_cast<uint32_t *>(ring_acc) + 16, warp_mem, warp, lane);
     }
     if constexpr (STAGE != 0) {
         // claimed one at a time, largest first: a CTA that drew a huge vertex takes fewer of them
@@ -1083,7 +1098,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
                 } else if (EXACT && g < n_walk) {
                     const uint32_t ul = __ldg(order + g);
                     const uint32_t deg = __ldg(row_ptr + ul + 1) - __ldg(row_ptr + ul);
-                    const float acc = px_walk16(px, g, deg, lane);
+                    const float acc = px_walk16(px, g, deg, T, lane);
                     put_features16(feat, g, acc, in, ul, deg, Wv, NWv, v_begin, scale, lane);
                     publish_feature(ready, g, lane);
                 } else {
@@ -1129,7 +1144,7 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
 template <int STAGE>
 constexpr size_t stage_smem_bytes() {
     constexpr StageDims D = stage_dims(STAGE);
-    return ((D.floats() + 3) / 4 * 4 + 44 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
+    return ((D.floats() + 3) / 4 * 4 + 48 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
 }
 
 // ---- schedule construction (graph upload time) -------------------------------------------
@@ -1269,7 +1284,9 @@ stage_tail_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restri
             float c[4] = {0.f, 0.f, 0.f, 0.f};
             for (int k = 0; k < 16; ++k) c[k & 3] = __fadd_rn(c[k & 3], __fmul_rn(f[0][k], Wc[k]));
             const float s = __fadd_rn(__fadd_rn(__fadd_rn(c[0], c[1]), __fadd_rn(c[2], c[3])), bc[0]);
-            out[ul] = sigmoid_ref<true>(s);
+            const float sg = sigmoid_ref<true>(s);
+            out[ul] = sg;
+            store_selection_key(peers, ul, sg);
         }
     }
 }

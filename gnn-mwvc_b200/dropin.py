@@ -43,6 +43,7 @@ class Dropin:
         L.gvcd_graph_size.argtypes = [C.c_void_p]
         L.gvcd_graph_mutate.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]
         L.gvcd_predict.argtypes = [C.c_void_p, C.c_void_p, _f32p, _f32p, C.POINTER(C.c_double)]
+        L.gvcd_predict_order.argtypes = [C.c_void_p, C.c_void_p, _f32p, _f32p, _u32p, C.POINTER(C.c_double)]
         self.L = L
         self.last_seconds = 0.0
 
@@ -81,6 +82,20 @@ class Dropin:
             raise RuntimeError("predict left `out` with an unexpected shape")
         self.last_seconds = sec.value
         return out
+
+
+    def predict_order(self, m, g, x, weight_scale: float):
+        """(scores, nodes): predict plus the vertex order the driver derives from it (src/GNN_VC.cpp:186-206),
+        sorted from the selection keys the stage-2 kernel left on the device."""
+        self.L.gvcd_model_set_weight_scale(m, float(weight_scale))
+        n = self.graph_size(g)
+        x = np.ascontiguousarray(x, np.float32).ravel()
+        out = np.empty(n, np.float32)
+        nodes = np.empty(n, np.uint32)
+        sec = C.c_double()
+        self.L.gvcd_predict_order(m, g, _p(x, _f32p), _p(out, _f32p), _p(nodes, _u32p), C.byref(sec))
+        self.last_seconds = sec.value
+        return out, nodes
 
 
 def model_text(layers, name="MWVC_Model") -> str:

@@ -13,12 +13,17 @@
 // extraction from the reduction_graph, upload, forward, scores back into the host matrix.
 #include "gnn_inference.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <numeric>
 #include <sstream>
 #include <string>
 #include <utility>
 #include <vector>
+
+#include "gvc.h"
+#include "gvc_host_ctx.hpp"
 
 namespace {
 struct dropin_graph {
@@ -82,6 +87,47 @@ int gvcd_predict(void *mh, void *gh, const float *x, float *scores, double *seco
     m->predict(d->in, d->out, d->g);
     if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (d->out.get_height() != n || (n && d->out.get_width() != 1)) return -1;
+    for (uint32_t u = 0; u < n; ++u) scores[u] = d->out(u, 0);
+    return 0;
+}
+
+// predict, then the vertex order src/GNN_VC.cpp:186-206 derives from it: nodes = 0..N-1 sorted with the
+// driver's tolerance comparator.  The comparator's inputs -- min(out, 1 - out) and out > 0.5 -- are not
+// recomputed on the host: they come off the device, where the stage-2 kernel wrote them beside the scores
+// (gvc_last_keys).  Same std::sort, same initial order, same decisions => same
+// permutation as the driver's own sort (the comparator is not a strict weak order, so this only holds
+// because every decision input is bit-identical).
+int gvcd_predict_order(void *mh, void *gh, const float *x, float *scores, uint32_t *nodes, double *seconds) {
+    auto *m = static_cast<gnn::model *>(mh);
+    auto *d = static_cast<dropin_graph *>(gh);
+    const uint32_t n = d->g.size();
+    d->in.resize(n, 1);
+    for (uint32_t u = 0; u < n; ++u) d->in(u, 0) = x[u];
+    const auto t0 = std::chrono::steady_clock::now();
+    m->predict(d->in, d->out, d->g);
+    std::vector<float> key(n);
+    std::vector<unsigned char> above(n);
+    if (n) {
+        const int rc = gvc_last_keys(gvc_host::context(), key.data(), above.data());
+        if (rc != 0) gvc_host::die("gvc_last_keys", rc);
+    }
+    std::vector<uint32_t> w(n), deg(n);
+    for (uint32_t u = 0; u < n; ++u) { w[u] = d->g.W(u); deg[u] = (uint32_t)(d->g.end(u) - d->g.begin(u)); }
+    std::iota(nodes, nodes + n, 0u);
+    const float eps = 0.0001f;
+    std::sort(nodes, nodes + n, [&](uint32_t a, uint32_t b) {
+        const float ka = key[a], kb = key[b];
+        if (ka < (kb + eps) && ka > (kb - eps)) {                  // within tolerance: side, then weight, then degree
+            const bool a_up = above[a], b_up = above[b];
+            const bool a_down = !a_up && ka != 0.5f, b_down = !b_up && kb != 0.5f;   // out < 0.5 (key == 0.5 <=> out == 0.5)
+            if (a_down && b_up) return true;
+            if (a_up && b_up) return w[a] < w[b] || (w[a] == w[b] && deg[a] > deg[b]);
+            if (a_down && b_down) return w[a] > w[b] || (w[a] == w[b] && deg[a] < deg[b]);
+            return false;
+        }
+        return ka < kb;
+    });
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (uint32_t u = 0; u < n; ++u) scores[u] = d->out(u, 0);
     return 0;
 }

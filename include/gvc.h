@@ -166,6 +166,21 @@ int gvc_forward(gvc_ctx *ctx, const float *x, float weight_scale, float *scores,
 int gvc_forward_device(gvc_ctx *ctx, const float *d_x, float weight_scale, float *d_scores,
                        int mode);
 
+/* The forward plus what the caller's vertex selection is computed from.  After
+ * predict, src/GNN_VC.cpp:194-206 orders the vertices by min(out, 1 - out) with an eps-tolerance
+ * comparator that also looks at out > 0.5; the stage-2 kernel writes both beside the scores:
+ *   keys[u] = std::min(out(u,0), 1.0f - out(u,0))    side[u] = out(u,0) > 0.5f
+ * evaluated in fp32 exactly as the comparator evaluates them, so a sort fed with them gives the
+ * reference's order (host/gvc_dropin_capi.cpp gvcd_predict_order).  GNN_VC architecture only.
+ * Host buffers of n entries each / device buffers of v_end - v_begin entries each. */
+int gvc_forward_keys(gvc_ctx *ctx, const float *x, float weight_scale, float *scores, float *keys,
+                     unsigned char *side, int mode);
+int gvc_forward_device_keys(gvc_ctx *ctx, const float *d_x, float weight_scale, float *d_scores,
+                            float *d_keys, unsigned char *d_side, int mode);
+/* gvc_forward (what model::predict calls) leaves the keys of its forward on the device as a
+ * by-product; this fetches them (n entries each) without running anything again. */
+int gvc_last_keys(gvc_ctx *ctx, float *keys, unsigned char *side);
+
 /* One fused stage of the GNN_VC architecture on this context's shard, DEVICE
  * buffers, enqueued on the context's stream:
  *   stage 0: graph layer (w=1)  + 5->32->32->16   d_in = x  [n_global]      -> d_out = h1 [n_global x 16]
@@ -240,6 +255,11 @@ int gvc_set_stream(gvc_ctx *ctx, void *stream);
 int gvc_sync(gvc_ctx *ctx);
 /* Number of kernels this context has launched so far. */
 uint64_t gvc_launch_count(const gvc_ctx *ctx);
+/* Statistics of the exact-mode parallel hub sums of the LAST stage launched (csrc/gvc_px.cuh):
+ * out8 = {vertices handled that way, their 4096-entry chunks, -, batches that fell back to the
+ * element-wise chain, -, SM cycles / 1024 the walks waited for their chunks, SM cycles / 1024 the walks
+ * took, batches the quantiser marked}.  For tests and tools. */
+int gvc_debug_px(gvc_ctx *ctx, uint32_t *out8);
 /* Device buffers of the last forward (h1/h2: n_global x 16), for tests. */
 const float *gvc_debug_h(const gvc_ctx *ctx, int which);
 

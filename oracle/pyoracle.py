@@ -236,6 +236,7 @@ class Reference:
         L.ref_graph_csr.restype = C.c_uint64
         L.ref_graph_csr.argtypes = [C.c_void_p, _u64p, _u32p, _u32p, _u32p, C.POINTER(C.c_uint8)]
         L.ref_predict_on.argtypes = [C.c_void_p, C.c_void_p, _f32p, _f32p, C.c_int, C.POINTER(C.c_double)]
+        L.ref_selection_order.argtypes = [C.c_void_p, C.c_void_p, _f32p, _f32p, _u32p]
         self.L = L
         if threads:
             L.ref_blas_threads(threads)
@@ -348,6 +349,15 @@ class Reference:
         assert rc == 0 or n == 0, "predict returned an unexpected shape"
         self.last_seconds = sec.value
         return out
+
+    def selection_order(self, h, gh, x, scale):
+        """(scores, nodes): predict and the driver's sort of the vertices (src/GNN_VC.cpp:186-206)."""
+        self.L.ref_model_set_weight_scale(h, float(scale))
+        n = self.graph_size(gh)
+        x = np.ascontiguousarray(x, np.float32)
+        out, nodes = np.empty(n, np.float32), np.empty(n, np.uint32)
+        self.L.ref_selection_order(h, gh, _p(x, _f32p), _p(out, _f32p), _p(nodes, _u32p))
+        return out, nodes
 
     def graph_layer(self, n, eu, ev, weights, scale, x):
         x = np.ascontiguousarray(x, np.float32)

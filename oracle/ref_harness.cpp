@@ -17,6 +17,7 @@
 //   reduction_graph ctor       include/reduction_graph.hpp:103-128
 #include "gnn_inference.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <sstream>
@@ -227,6 +228,33 @@ int ref_predict_on(void *h, void *gh, const float *x, float *out, int reps, doub
     if (seconds) *seconds = best;
     if (gs->res.get_height() != n || (n && gs->res.get_width() != 1)) return -1;
     for (uint32_t u = 0; u < n; u++) out[u] = gs->res(u, 0);
+    return 0;
+}
+
+// What the driver does with the scores (src/GNN_VC.cpp:186-206): nodes = 0..N-1, predict, then std::sort
+// with its tolerance comparator on min(out, 1 - out), ties decided by the side of 0.5, the weight and the
+// degree.  Restated here over whichever predict this harness is built on, as the checker for the
+// device-side selection keys.
+int ref_selection_order(void *h, void *gh, const float *x, float *out, uint32_t *nodes) {
+    auto *s = static_cast<ref_state *>(h);
+    auto *gs = static_cast<ref_graph_state *>(gh);
+    auto &g = gs->g;
+    const uint32_t n = g.size();
+    gs->in.resize(n, 1);
+    for (uint32_t u = 0; u < n; u++) gs->in(u, 0) = x[u];
+    s->m.predict(gs->in, gs->res, g);
+    const matrix &o = gs->res;
+    for (uint32_t u = 0; u < n; u++) { nodes[u] = u; out[u] = o(u, 0); }
+    std::sort(nodes, nodes + n, [&](uint32_t a, uint32_t b) {
+        const float pa = o(a, 0), pb = o(b, 0);
+        const float ka = std::min(pa, 1.0f - pa), kb = std::min(pb, 1.0f - pb), tol = 0.0001f;
+        const bool close = ka < (kb + tol) && ka > (kb - tol);
+        if (!close) return ka < kb;
+        if (pa < 0.5 && pb > 0.5) return true;
+        if (pa > 0.5 && pb > 0.5) return g.W(a) < g.W(b) || (g.W(a) == g.W(b) && g.D(a) > g.D(b));
+        if (pa < 0.5 && pb < 0.5) return g.W(a) > g.W(b) || (g.W(a) == g.W(b) && g.D(a) < g.D(b));
+        return false;
+    });
     return 0;
 }
 

@@ -14,7 +14,7 @@ def seq_sum(v):
 def expo(x):   # floor(log2(x)) for positive normal float32, from the bits
     return ((np.asarray(x, f32).view(np.uint32) >> 23) & 0xFF).astype(np.int32) - 127
 
-def px_sum(v, BATCH=64, delta=1e-3, stats=None):
+def px_sum(v, BATCH=64, delta=1.0 / 4096, stats=None):
     v = np.asarray(v, f32)
     n = len(v); nb = (n + BATCH - 1) // BATCH
     # pass A: approximate batch sums (any order), prefix in double
@@ -24,6 +24,9 @@ def px_sum(v, BATCH=64, delta=1e-3, stats=None):
     D = np.zeros(nb, f32); clean = np.zeros(nb, bool); E = np.zeros(nb, np.int32)
     for b in range(nb):
         vb = v[b*BATCH:(b+1)*BATCH]
+        if not np.any(vb != 0):                           # an all-zero batch adds nothing whatever the running sum is
+            D[b] = 0; clean[b] = True; E[b] = -999
+            continue
         lo, hi = P[b] * (1 - delta), P[b+1] * (1 + delta)
         if not (lo >= 2.0**-125 and hi >= lo and hi < 2.0**127):              # zero / tiny / NaN / decreasing prefix: no prediction
             continue
@@ -41,10 +44,10 @@ def px_sum(v, BATCH=64, delta=1e-3, stats=None):
     # pass C: sequential composition with verification
     acc = f32(0); slow = 0
     for b in range(nb):
-        good = clean[b] and acc > 0 and expo(acc) == E[b]
+        good = clean[b] and (E[b] == -999 or (acc > 0 and expo(acc) == E[b]))
         if good:
             nxt = f32(acc + D[b])
-            good = nxt < f32(2.0**(E[b]+1))
+            good = E[b] == -999 or nxt < f32(2.0**(E[b]+1))
         if good:
             acc = nxt
         else:

@@ -64,3 +64,33 @@ def test_config5_full_run_on_shrinking_graphs(tmp_path):
     assert outs["gpu"][0] == outs["ref"][0], "cover cost differs"
     assert outs["gpu"][1] == outs["ref"][1], "cover differs"
     assert "predict calls" in outs["gpu"][2]          # the forward really went through libgvc
+
+
+@pytest.mark.parametrize("maker", [lambda: graphs.er10k_fixture(), lambda: graphs.er_graph(60_000, 300_000, seed=5)],
+                         ids=["er10k", "er60k"])
+def test_selection_order_from_device_keys(maker):
+    """the stage-2 kernel leaves min(out, 1 - out) and out > 0.5 on the device; the
+    vertex order sorted from them (host/gvc_dropin_capi.cpp gvcd_predict_order) must be the permutation the
+    driver's own std::sort produces from the reference's scores (src/GNN_VC.cpp:186-206, restated in
+    oracle/ref_harness.cpp over the unmodified reference)."""
+    import numpy as np
+    from gnn_mwvc_b200 import capi, dropin
+    from oracle import pyoracle as po
+    if not po.REF_SO.exists() or not dropin.LIB_PATH.exists():
+        pytest.skip("needs oracle/_ref and the drop-in binding (built where /root/reference exists)")
+    g = maker()
+    eu, ev = g.edges_numpy()
+    W = g.numpy()[2]
+    x = W.astype(np.float32) / np.float32(200.0)
+    layers = capi.load_model_npz(GOLDEN / "mwvc_model.npz")
+    ref = po.Reference(threads=1)
+    hr = ref.model(po.layers_to_text(layers))
+    gr = ref.graph_create(g.n, eu, ev, W)
+    want_scores, want_nodes = ref.selection_order(hr, gr, x, 200.0)
+    d = dropin.Dropin()
+    m = d.model(dropin.model_text(layers))
+    gh = d.graph(g.n, eu, ev, W)
+    scores, nodes = d.predict_order(m, gh, x, 200.0)
+    assert np.array_equal(scores.view(np.uint32), want_scores.view(np.uint32))
+    assert np.array_equal(nodes, want_nodes), f"{int((nodes != want_nodes).sum())} of {g.n} positions differ"
+    assert sorted(nodes.tolist()) == list(range(g.n))

@@ -51,6 +51,12 @@ with torch.cuda.stream(stream):
                 e1.synchronize()
                 if it >= 3:
                     ms[st].append(e0.elapsed_time(e1))
+        if mode == pkg.MODE_EXACT:
+            px = []
+            for st, (p, q) in enumerate(((x, h1), (h1, h2), (h2, sc))):
+                ctx.stage_device(st, p, q, 200.0, mode)
+                px.append(ctx.px_stats())
+            out["px"] = px
         out[name + "_ms"] = [round(float(np.mean(m)), 4) for m in ms]
         out[name + "_ns_per_neighbour"] = [round(float(np.mean(m)) * 1e6 / D, 2) for m in ms]
 print(json.dumps(out), flush=True)

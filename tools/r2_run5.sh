@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python tools/chain_probe.py 262144 > gpurun_out/r2_chain_probe_262144_px2.json 2> gpurun_out/r2_chain_probe5.err; cat gpurun_out/r2_chain_probe_262144_px2.json
+timeout 300 python tools/chain_probe.py 65536 200000 > gpurun_out/r2_chain_probe_65536_busy_px2.json 2>> gpurun_out/r2_chain_probe5.err; cat gpurun_out/r2_chain_probe_65536_busy_px2.json
+timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_run5.json 2> gpurun_out/r2_bench_run5.err; echo "bench rc=$?"
+timeout 900 python bench.py --scale 23 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_scale23_1gpu_exact_px2.json 2> gpurun_out/r2_scale23_px2.err
+python - <<'PY'
+import json
+for f in ("gpurun_out/r2_bench_run5.json", "gpurun_out/r2_scale23_1gpu_exact_px2.json"):
+    try:
+        d=json.loads([l for l in open(f) if l.startswith("{")][-1]); r=d["roofline"]
+        print(f, "ms/step %.3f"%d["ms_per_step"], "Gedges/s %.2f"%(d["value"]/1e9), "stage_ms", [round(x,3) for x in r["stage_ms"]], "fwd_frac %.3f"%r["forward_frac"], "e2e ms %.3f first %.1f"%(d["e2e"]["ms_per_step"], d["e2e"].get("first_call_ms", 0)), d["other_mode"]["ms_per_step"])
+    except Exception as e: print(f, "FAILED", e)
+PY

@@ -62,6 +62,14 @@ SIGNATURES = {
     "gvc_sigmoid_host": (C.c_int, [C.c_void_p, C.c_uint64, _f32p, _f32p, C.c_int]),
     "gvc_sgemm_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, _f32p, C.c_uint64,
                                  _f32p, C.c_uint64, C.c_float, _f32p, C.c_uint64]),
+    "gvc_group_create": (C.c_int, [C.POINTER(C.c_void_p), _i32p, C.c_int]),
+    "gvc_group_destroy": (None, [C.c_void_p]),
+    "gvc_group_size": (C.c_int, [C.c_void_p]),
+    "gvc_group_model_upload": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p, _i32p, C.POINTER(_f32p), C.POINTER(_f32p)]),
+    "gvc_group_model_weight_scales": (C.c_int, [C.c_void_p, C.c_int, _f32p]),
+    "gvc_group_graph_upload": (C.c_int, [C.c_void_p, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
+    "gvc_group_bounds": (C.c_int, [C.c_void_p, _u32p]),
+    "gvc_group_forward": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, C.c_int]),
     "gvc_stream": (C.c_void_p, [C.c_void_p]),
     "gvc_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gvc_sync": (C.c_int, [C.c_void_p]),
@@ -383,6 +391,68 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.gvc_launch_count(self.h))
+
+
+class Group:
+    """gvc_group: one context per device in THIS process, the forward sharded over them."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        h = C.c_void_p()
+        d = (C.c_int * len(devices))(*devices)
+        self._check(self.lib.gvc_group_create(C.byref(h), d, len(devices)))
+        self.h = h
+        self.n = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GvcError(f"libgvc error {rc}: {self.lib.gvc_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gvc_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def model_upload(self, layers):
+        n = len(layers)
+        kinds = (C.c_int * n)(*[int(k) for k, _, _ in layers])
+        rows, cols = (C.c_int * n)(), (C.c_int * n)()
+        Wp, bp = (_f32p * n)(), (_f32p * n)()
+        keep = []
+        for i, (k, W, b) in enumerate(layers):
+            if k == LINEAR:
+                W = _np(W, np.float32)
+                b = _np(b, np.float32).ravel()
+                rows[i], cols[i] = W.shape
+                Wp[i], bp[i] = W.ctypes.data_as(_f32p), b.ctypes.data_as(_f32p)
+                keep += [W, b]
+        self._check(self.lib.gvc_group_model_upload(self.h, n, kinds, rows, cols, Wp, bp))
+
+    def graph_upload(self, row_ptr, col, W, NW):
+        row_ptr, col = _np(row_ptr, np.uint64), _np(col, np.uint32)
+        W, NW = _np(W, np.uint32), _np(NW, np.uint32)
+        self.n = len(row_ptr) - 1
+        self._check(self.lib.gvc_group_graph_upload(self.h, self.n, _ptr(row_ptr, _u64p), _ptr(col, _u32p), _ptr(W, _u32p), _ptr(NW, _u32p)))
+
+    @property
+    def bounds(self):
+        b = np.zeros(self.lib.gvc_group_size(self.h) + 1, np.uint32)
+        self._check(self.lib.gvc_group_bounds(self.h, _ptr(b, _u32p)))
+        return b.tolist()
+
+    def forward(self, x, weight_scale: float, mode: int = MODE_EXACT) -> np.ndarray:
+        x = _np(x, np.float32).ravel()
+        if x.size != self.n:
+            raise GvcError(f"x has {x.size} entries, graph has {self.n} vertices")
+        out = np.empty(self.n, np.float32)
+        self._check(self.lib.gvc_group_forward(self.h, _ptr(x, _f32p), float(weight_scale), _ptr(out, _f32p), mode))
+        return out
 
 
 def load_model_npz(path):

@@ -541,10 +541,21 @@ int build_schedule(gvc_ctx *c) {
     GVC_CUDA(cudaMemcpyAsync(hist, c->d_bins.p, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));
     uint32_t pos = 0, n_ring = 0, n_pre = 0, n_giant1 = 0, n_px = 0;
+    // Which vertices get their sequential sums emulated in parallel (gvc_px.cuh)?  Only those whose
+    // chain would otherwise be the critical path of a stage: the emulation gathers a hub's rows twice
+    // and keeps a scratch copy, so a 20 000-neighbour vertex of a 258 M-entry shard (chain 0.07 ms in a
+    // 4.6 ms stage) is better left to one ring CTA, while the same vertex in a 30 M-entry shard is not.
+    // Chain ~3.4 ns per neighbour against ~0.016 ns per adjacency entry of the shard for everything else.
+    const uint64_t px_deg = std::max<uint64_t>(kPxMinDeg, c->nnz / kPxNnzPerNeighbour);
+    auto bin_min_degree = [](int b) -> uint64_t {                // inverse of degree_bin: smallest degree of bin b
+        if (b < 4) return (uint64_t)b;
+        const int lg = (b + 4) / 4, frac = (b + 4) % 4;
+        return (uint64_t)(4 + frac) << (lg - 2);
+    };
     for (int b = kNumDegBins - 1; b >= 0; --b) {          // descending degree
         if (b == degree_bin(kRingMinDeg) - 1) n_ring = pos;
         if (b == degree_bin(kGiant1MinDeg) - 1) n_giant1 = pos;
-        if (b == degree_bin(kPxMinDeg) - 1) n_px = pos;
+        if (bin_min_degree(b) >= px_deg) n_px = pos + hist[b];       // bins are walked by descending degree
         if (b == degree_bin(kMidMinDeg) - 1) n_pre = pos;
         start[b] = pos;
         pos += hist[b];
@@ -1650,6 +1661,206 @@ int gvc_sgemm_host(gvc_ctx *c, int ta, int tb, uint64_t m, uint64_t n, uint64_t 
     c->launches++;
     GVC_CUDA(cudaMemcpyAsync(Cm, dC, c_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     GVC_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ================================ several GPUs, one process =======================================
+// SURVEY.md 8(e) behind one call: vertex-range shards over the devices of a group, every shard a
+// gvc_ctx of its own.  The row exchange is the stage kernels' own (each finished row is stored into
+// the h buffers of the devices that own a neighbour, over NVLink peer access), and what remains
+// between two stages -- "every device has finished its stage" -- is expressed with CUDA events that
+// the streams wait on; the host thread never blocks inside a forward and no collective library is
+// involved.
+struct gvc_group {
+    std::vector<gvc_ctx *> ctx;
+    std::vector<uint32_t> bounds;            // vertex ranges of the shards: [bounds[d], bounds[d + 1])
+    std::vector<cudaEvent_t> done;           // per device: "my stage kernel (and its peer stores) has finished"
+    std::vector<uint64_t> rp_tmp;            // host scratch for a shard's rebased offsets
+    uint32_t n = 0;
+    bool have_graph = false;
+};
+
+namespace {
+int group_check(const gvc_group *g) {
+    if (!g || g->ctx.empty()) return fail(GVC_ERR_ARG, "null group");
+    return 0;
+}
+}  // namespace
+
+int gvc_group_create(gvc_group **out, const int *devices, int n_devices) {
+    if (!out || !devices) return fail(GVC_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > kMaxPeers + 1) return fail(GVC_ERR_UNSUPPORTED, "%d devices; 1..%d", n_devices, kMaxPeers + 1);
+    gvc_group *g = new (std::nothrow) gvc_group();
+    if (!g) return fail(GVC_ERR_ALLOC, "out of host memory");
+    int rc = 0;
+    for (int d = 0; d < n_devices && !rc; ++d) {
+        gvc_ctx *c = nullptr;
+        if ((rc = gvc_ctx_create(&c, devices[d]))) break;
+        g->ctx.push_back(c);
+    }
+    // every device stores rows into every other device's buffers: peer access both ways
+    for (int a = 0; a < (int)g->ctx.size() && !rc; ++a)
+        for (int b = 0; b < (int)g->ctx.size() && !rc; ++b) {
+            const int da = g->ctx[a]->device, db = g->ctx[b]->device;
+            if (da == db) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, da, db);
+            if (!can) { rc = fail(GVC_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", da, db); break; }
+            cudaSetDevice(da);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = fail(1000 + (int)e, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    for (size_t d = 0; d < g->ctx.size() && !rc; ++d) {
+        cudaEvent_t ev = nullptr;
+        cudaSetDevice(g->ctx[d]->device);
+        const cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) rc = fail(1000 + (int)e, "cudaEventCreate: %s", cudaGetErrorString(e));
+        else g->done.push_back(ev);
+    }
+    if (rc) { gvc_group_destroy(g); return rc; }
+    *out = g;
+    return 0;
+}
+
+void gvc_group_destroy(gvc_group *g) {
+    if (!g) return;
+    for (auto *c : g->ctx) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    for (size_t d = 0; d < g->done.size(); ++d) { cudaSetDevice(g->ctx[d]->device); cudaEventDestroy(g->done[d]); }
+    for (auto *c : g->ctx) gvc_ctx_destroy(c);
+    delete g;
+}
+
+int gvc_group_size(const gvc_group *g) { return g ? (int)g->ctx.size() : 0; }
+
+int gvc_group_model_upload(gvc_group *g, int n_layers, const int *kinds, const int *rows, const int *cols,
+                           const float *const *W, const float *const *bias) {
+    int rc;
+    if ((rc = group_check(g))) return rc;
+    for (auto *c : g->ctx)
+        if ((rc = gvc_model_upload(c, n_layers, kinds, rows, cols, W, bias))) return rc;
+    if (!g->ctx[0]->fused) return fail(GVC_ERR_UNSUPPORTED, "sharded forwards need the GNN_VC architecture (fused stage kernels)");
+    return 0;
+}
+
+int gvc_group_model_weight_scales(gvc_group *g, int n_graph_layers, const float *scales) {
+    int rc;
+    if ((rc = group_check(g))) return rc;
+    for (auto *c : g->ctx)
+        if ((rc = gvc_model_weight_scales(c, n_graph_layers, scales))) return rc;
+    return 0;
+}
+
+// Whole graph in, shards out: contiguous vertex ranges with about the same number of adjacency entries
+// plus a per-vertex cost (the dense chain), boundaries at multiples of 32.
+int gvc_group_graph_upload(gvc_group *g, uint32_t n, const uint64_t *row_ptr, const uint32_t *col, const uint32_t *W,
+                           const uint32_t *NW) {
+    int rc;
+    if ((rc = group_check(g))) return rc;
+    if (n && (!row_ptr || !W || !NW)) return fail(GVC_ERR_ARG, "null graph arrays");
+    const int P = (int)g->ctx.size();
+    g->have_graph = false;
+    g->n = n;
+    g->bounds.assign(P + 1, n);
+    g->bounds[0] = 0;
+    const uint64_t nnz = n ? row_ptr[n] : 0;
+    const uint64_t per_vertex = 24;                                   // a vertex costs about as much as 24 adjacency entries
+    const double total = (double)nnz + (double)per_vertex * n;
+    uint32_t u = 0;
+    for (int d = 1; d < P; ++d) {
+        const double want = total * d / P;
+        // first vertex whose prefix cost reaches `want` (binary search on row_ptr[u] + per_vertex * u)
+        uint32_t lo = u, hi = n;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if ((double)row_ptr[mid] + (double)per_vertex * mid < want) lo = mid + 1; else hi = mid;
+        }
+        u = std::min<uint32_t>(n, (lo + 31) / 32 * 32);
+        g->bounds[d] = std::max(u, g->bounds[d - 1]);
+    }
+    // peers: device d mirrors its rows into the buffers of every other device that owns a neighbour
+    for (int d = 0; d < P; ++d) {
+        gvc_ctx *c = g->ctx[d];
+        const uint32_t vb = g->bounds[d], ve = g->bounds[d + 1], nl = ve - vb;
+        g->rp_tmp.resize((size_t)nl + 1);
+        for (uint32_t i = 0; i <= nl; ++i) g->rp_tmp[i] = row_ptr[vb + i] - row_ptr[vb];
+        if ((rc = gvc_graph_upload_shard(c, n, vb, ve, g->rp_tmp.data(), col ? col + row_ptr[vb] : nullptr, W + vb, NW + vb))) return rc;
+    }
+    for (int d = 0; d < P && P > 1; ++d) {
+        gvc_ctx *c = g->ctx[d];
+        float *p1[kMaxPeers], *p2[kMaxPeers];
+        int peer_of_part[kMaxPeers + 1];
+        int q = 0;
+        for (int o = 0; o < P; ++o) {
+            if (o == d) { peer_of_part[o] = -1; continue; }
+            p1[q] = g->ctx[o]->d_h1.p;
+            p2[q] = g->ctx[o]->d_h2.p;
+            peer_of_part[o] = q++;
+        }
+        if ((rc = gvc_stage_peers(c, 0, q, p1))) return rc;
+        if ((rc = gvc_stage_peers(c, 1, q, p2))) return rc;
+        if ((rc = gvc_peer_owners(c, P, g->bounds.data(), peer_of_part))) return rc;
+    }
+    g->have_graph = true;
+    return 0;
+}
+
+int gvc_group_bounds(const gvc_group *g, uint32_t *bounds_out) {
+    if (!g || !bounds_out) return fail(GVC_ERR_ARG, "null argument");
+    for (size_t i = 0; i < g->bounds.size(); ++i) bounds_out[i] = g->bounds[i];
+    return 0;
+}
+
+// gnn::model::predict over the group: x replicated, three stages with "all devices done" between them,
+// every device's score slice copied into scores[bounds[d] ..).
+int gvc_group_forward(gvc_group *g, const float *x, float scale, float *scores, int mode) {
+    int rc;
+    if ((rc = group_check(g))) return rc;
+    if (!g->have_graph) return fail(GVC_ERR_STATE, "no graph uploaded");
+    if (mode != GVC_MODE_EXACT && mode != GVC_MODE_FAST) return fail(GVC_ERR_ARG, "bad mode %d", mode);
+    const uint32_t n = g->n;
+    if (!n) return 0;
+    if (!x || !scores) return fail(GVC_ERR_ARG, "null buffer");
+    const int P = (int)g->ctx.size();
+    for (auto *c : g->ctx) {
+        if ((rc = use_device(c))) return rc;
+        GVC_CUDA(cudaMemcpyAsync(c->d_x.p, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    auto all_done = [&]() -> int {          // every stream waits until every device's stage (and its peer stores) has finished
+        for (int d = 0; d < P; ++d) {
+            GVC_CUDA(cudaSetDevice(g->ctx[d]->device));
+            GVC_CUDA(cudaEventRecord(g->done[d], g->ctx[d]->stream));
+        }
+        for (int d = 0; d < P; ++d) {
+            GVC_CUDA(cudaSetDevice(g->ctx[d]->device));
+            for (int o = 0; o < P; ++o)
+                if (o != d) GVC_CUDA(cudaStreamWaitEvent(g->ctx[d]->stream, g->done[o], 0));
+        }
+        return 0;
+    };
+    // nobody may still be reading h1/h2 of an earlier forward when the first peer stores arrive
+    if ((rc = all_done())) return rc;
+    for (int stage = 0; stage < 3; ++stage) {
+        for (auto *c : g->ctx) {
+            const float s = c->layer_scales.size() == 3 ? c->layer_scales[stage] : scale;
+            const float *in = stage == 0 ? c->d_x.p : stage == 1 ? c->d_h1.p : c->d_h2.p;
+            float *out = stage == 0 ? c->d_h1.p : stage == 1 ? c->d_h2.p : c->d_scores.p;
+            if ((rc = gvc_stage_device(c, stage, in, out, s, mode))) return rc;
+        }
+        if (stage < 2 && (rc = all_done())) return rc;
+    }
+    for (int d = 0; d < P; ++d) {
+        gvc_ctx *c = g->ctx[d];
+        const uint32_t vb = g->bounds[d], nl = g->bounds[d + 1] - vb;
+        if (!nl) continue;
+        GVC_CUDA(cudaSetDevice(c->device));
+        GVC_CUDA(cudaMemcpyAsync(scores + vb, c->d_scores.p, (size_t)nl * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    for (auto *c : g->ctx) {
+        GVC_CUDA(cudaSetDevice(c->device));
+        GVC_CUDA(cudaStreamSynchronize(c->stream));
+    }
     return 0;
 }
 

@@ -97,6 +97,10 @@ constexpr uint32_t kRingMinDeg = GVC_RING_MIN_DEG;
 #define GVC_PX_MIN_DEG 16384
 #endif
 constexpr uint32_t kPxMinDeg = GVC_PX_MIN_DEG;           // exact mode: >= this, the sequential sum is emulated in parallel (gvc_px.cuh)
+#ifndef GVC_PX_NNZ_PER_NEIGHBOUR
+#define GVC_PX_NNZ_PER_NEIGHBOUR 1000
+#endif
+constexpr uint64_t kPxNnzPerNeighbour = GVC_PX_NNZ_PER_NEIGHBOUR;   // ... and at least (shard's adjacency entries) / this
 constexpr uint32_t kGiant1MinDeg = GVC_GIANT1_MIN_DEG;   // stage 0 (w = 1): >= one warp per vertex, below one lane    // >= : ring task (whole CTA)
 constexpr uint32_t kMidMinDeg = GVC_MID_MIN_DEG;      // >= : mid task (8 vertices per warp), below: 32-vertex tiles
 constexpr int kNumDegBins = 132;

@@ -69,7 +69,7 @@ csr_view extract_csr(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g) {
     static std::vector<uint64_t> pg_row_ptr;
     static std::vector<uint32_t> pg_col, pg_w, pg_nw;
     const uint64_t vertex_bytes = 16ull * ((uint64_t)n + 1);
-    bool pinned = vertex_bytes <= staging_max &&
+    bool pinned = ctx && vertex_bytes <= staging_max &&
                   gvc_graph_staging(ctx, n, 0, &s.row_ptr, &s.col, &s.w, &s.nw) == 0;
     if (!pinned) {
         if (pg_row_ptr.size() < (size_t)n + 1) { pg_row_ptr.resize((size_t)n + 1); pg_w.resize(n); pg_nw.resize(n); }
@@ -312,8 +312,9 @@ int kind_of(const component &c) {
                       c);
 }
 
-void upload_model_if_stale(gvc_ctx *ctx, const void *owner, const std::vector<component> &layers) {
-    static model_key current;
+void upload_model_if_stale(gvc_ctx *ctx, gvc_group *grp, const void *owner, const std::vector<component> &layers) {
+    static model_key current_ctx, current_grp;
+    model_key &current = grp ? current_grp : current_ctx;
     uint64_t h = 1469598103934665603ull;
     for (auto &c : layers) {
         const int k = kind_of(c);
@@ -339,7 +340,8 @@ void upload_model_if_stale(gvc_ctx *ctx, const void *owner, const std::vector<co
             b[i] = cdata(l->bias);
         }
     }
-    const int rc = gvc_model_upload(ctx, n, kinds.data(), rows.data(), cols.data(), W.data(), b.data());
+    const int rc = grp ? gvc_group_model_upload(grp, n, kinds.data(), rows.data(), cols.data(), W.data(), b.data())
+                       : gvc_model_upload(ctx, n, kinds.data(), rows.data(), cols.data(), W.data(), b.data());
     if (rc != 0) gvc_host::die("gvc_model_upload", rc);
     current.owner = owner;
     current.hash = h;
@@ -414,8 +416,10 @@ void model::predict(const matrix &in, matrix &out, const reduction_graph<Tn, Tw>
     const Tn n = g.size();
     out.resize(n, 1);
     if (n == 0 || layers.empty()) return;
-    gvc_ctx *ctx = gvc_host::context();
-    upload_model_if_stale(ctx, this, layers);
+    // graphs of GVC_MULTI_MIN_VERTICES vertices and more are sharded over the devices of GVC_DEVICES
+    gvc_group *grp = gvc_host::shard_over_devices(n) ? gvc_host::group() : nullptr;
+    gvc_ctx *ctx = grp ? nullptr : gvc_host::context();
+    upload_model_if_stale(ctx, grp, this, layers);
 
     // every graph layer divides by its OWN WEIGHT_SCALE (src/gnn_inference.cpp:38-40); after
     // set_weight_scale they are all equal and one scalar does, a model built with add_layer may differ
@@ -426,9 +430,29 @@ void model::predict(const matrix &in, matrix &out, const reduction_graph<Tn, Tw>
     if (!scales.empty()) scale = scales[0];
     const bool uniform = std::all_of(scales.begin(), scales.end(), [&](float v) { return v == scale; });
     {
-        const int rc0 = uniform ? gvc_model_weight_scales(ctx, 0, nullptr)
-                                : gvc_model_weight_scales(ctx, (int)scales.size(), scales.data());
+        const int ns = uniform ? 0 : (int)scales.size();
+        const int rc0 = grp ? gvc_group_model_weight_scales(grp, ns, ns ? scales.data() : nullptr)
+                            : gvc_model_weight_scales(ctx, ns, ns ? scales.data() : nullptr);
         if (rc0 != 0) gvc_host::die("gvc_model_weight_scales", rc0);
+    }
+    if (grp) {
+        // vertex-range shards over several GPUs in this process: the CSR is compacted on
+        // the host, every device gets its range, the stage kernels exchange rows through peer memory
+        predict_profile &pg = profile();
+        const double g0 = now_s();
+        const csr_view s = extract_csr(nullptr, g);
+        const double g1 = now_s();
+        int rc = gvc_group_graph_upload(grp, n, s.row_ptr, s.col, s.w, s.nw);
+        if (rc != 0) gvc_host::die("gvc_group_graph_upload", rc);
+        const double g2 = now_s();
+        rc = gvc_group_forward(grp, cdata(in), scale, mdata(out), gvc_host::mode());
+        if (rc != 0) gvc_host::die("gvc_group_forward", rc);
+        const double g3 = now_s();
+        pg.calls++; pg.extract += g1 - g0; pg.upload += g2 - g1; pg.forward += g3 - g2;
+        if (pg.on)
+            std::fprintf(stderr, "gvc profile: predict n=%u entries=%zu on %d devices: extract %.2f ms upload %.2f ms forward %.2f ms\n",
+                         n, (size_t)s.nnz, gvc_group_size(grp), 1e3 * (g1 - g0), 1e3 * (g2 - g1), 1e3 * (g3 - g2));
+        return;
     }
 
     predict_profile &pf = profile();

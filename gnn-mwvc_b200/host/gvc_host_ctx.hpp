@@ -4,6 +4,9 @@
 // created lazily at first use.  Environment:
 //   GVC_DEVICE  CUDA ordinal (default 0)
 //   GVC_MODE    "exact" (default, bit-identical scores) or "fast"
+//   GVC_DEVICES "0,1,2,3": predict() shards graphs of at least GVC_MULTI_MIN_VERTICES vertices
+//               (default 2 000 000) over these devices (gvc_group, include/gvc.h); smaller graphs and
+//               everything else stay on the first of them
 // Errors follow the reference driver's convention of print-and-stop: the API is
 // void everywhere (include/gnn_inference.hpp:50), so a CUDA failure prints to
 // stderr and aborts.  There is no CPU fallback.
@@ -11,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "gvc.h"
 
@@ -21,15 +25,54 @@ namespace gvc_host {
     std::abort();
 }
 
+inline const std::vector<int> &devices() {
+    static const std::vector<int> list = [] {
+        std::vector<int> v;
+        if (const char *e = std::getenv("GVC_DEVICES")) {
+            for (const char *p = e; *p;) {
+                char *end = nullptr;
+                const long d = std::strtol(p, &end, 10);
+                if (end == p) break;
+                v.push_back((int)d);
+                p = *end == ',' ? end + 1 : end;
+            }
+        }
+        return v;
+    }();
+    return list;
+}
+
 inline gvc_ctx *context() {
     static gvc_ctx *ctx = [] {
         const char *dev = std::getenv("GVC_DEVICE");
         gvc_ctx *c = nullptr;
-        const int rc = gvc_ctx_create(&c, dev ? std::atoi(dev) : 0);
+        const int ordinal = dev ? std::atoi(dev) : (devices().empty() ? 0 : devices()[0]);
+        const int rc = gvc_ctx_create(&c, ordinal);
         if (rc != 0) die("gvc_ctx_create", rc);
         return c;
     }();
     return ctx;
+}
+
+// the group of GVC_DEVICES (null when fewer than two are named)
+inline gvc_group *group() {
+    static gvc_group *grp = [] {
+        gvc_group *g = nullptr;
+        if (devices().size() >= 2) {
+            const int rc = gvc_group_create(&g, devices().data(), (int)devices().size());
+            if (rc != 0) die("gvc_group_create", rc);
+        }
+        return g;
+    }();
+    return grp;
+}
+
+inline bool shard_over_devices(uint64_t n_vertices) {
+    static const uint64_t min_n = [] {
+        const char *e = std::getenv("GVC_MULTI_MIN_VERTICES");
+        return e ? std::strtoull(e, nullptr, 10) : 2000000ull;
+    }();
+    return devices().size() >= 2 && n_vertices >= min_n;
 }
 
 inline int mode() {

@@ -218,6 +218,29 @@ int gvc_stage_peers(gvc_ctx *ctx, int stage, int n_peers, float *const *d_out_pe
  * them.  The per-vertex peer lists are rebuilt with every graph upload; n_parts = 0 forgets them. */
 int gvc_peer_owners(gvc_ctx *ctx, int n_parts, const uint32_t *bounds, const int *peer_of_part);
 
+/* ---- several GPUs in ONE process: predict on a graph too large (or too slow) for one device -------
+ * SURVEY.md 8(e) behind one call, for a caller like gnn::model::predict (include/gnn_inference.hpp:50)
+ * that is a single thread of a single process: a group owns one context per device; the graph is cut
+ * into contiguous vertex ranges of about equal work; a forward runs the three stage kernels on every
+ * device, each storing the rows other devices read straight into their buffers (peer access over
+ * NVLink), with "every device has finished its stage" between two stages expressed as CUDA events
+ * the streams wait on.  Scores come back in vertex order, bit-identical to a one-device forward
+ * (per-vertex arithmetic does not depend on the sharding).  GNN_VC architecture only; devices may
+ * repeat (two shards on one GPU: how the path is tested where only one GPU is visible). */
+typedef struct gvc_group gvc_group;
+int gvc_group_create(gvc_group **out, const int *devices, int n_devices);
+void gvc_group_destroy(gvc_group *group);
+int gvc_group_size(const gvc_group *group);
+int gvc_group_model_upload(gvc_group *group, int n_layers, const int *kinds, const int *rows,
+                           const int *cols, const float *const *W, const float *const *bias);
+int gvc_group_model_weight_scales(gvc_group *group, int n_graph_layers, const float *scales);
+/* whole graph in (as gvc_graph_upload), shards out */
+int gvc_group_graph_upload(gvc_group *group, uint32_t n, const uint64_t *row_ptr, const uint32_t *col,
+                           const uint32_t *W, const uint32_t *NW);
+/* bounds_out[0 .. size]: the vertex ranges the last upload chose */
+int gvc_group_bounds(const gvc_group *group, uint32_t *bounds_out);
+int gvc_group_forward(gvc_group *group, const float *x, float weight_scale, float *scores, int mode);
+
 /* Single layers on device buffers, row counts explicit (generic path; also the
  * kernel-level parity tests).  in/out are row-major n x width. */
 int gvc_graph_layer_device(gvc_ctx *ctx, const float *d_in, int width, float *d_out,

@@ -96,6 +96,16 @@ int gvc_relu_host(gvc_ctx *, uint64_t, const float *, float *) { return 0; }
 int gvc_sigmoid_host(gvc_ctx *, uint64_t, const float *, float *, int) { return 0; }
 int gvc_sgemm_host(gvc_ctx *, int, int, uint64_t, uint64_t, uint64_t, const float *, uint64_t, const float *, uint64_t, float, float *, uint64_t) { return 0; }
 
+// the group entry points exist for the linker only (the mock never shards)
+struct gvc_group { int dummy; };
+int gvc_group_create(gvc_group **, const int *, int) { return 1; }
+void gvc_group_destroy(gvc_group *) {}
+int gvc_group_size(const gvc_group *) { return 0; }
+int gvc_group_model_upload(gvc_group *, int, const int *, const int *, const int *, const float *const *, const float *const *) { return 1; }
+int gvc_group_model_weight_scales(gvc_group *, int, const float *) { return 1; }
+int gvc_group_graph_upload(gvc_group *, uint32_t, const uint64_t *, const uint32_t *, const uint32_t *, const uint32_t *) { return 1; }
+int gvc_group_forward(gvc_group *, const float *, float, float *, int) { return 1; }
+
 // what the last upload delivered: sizes first (nulls), then the arrays
 uint64_t mock_last_graph(uint64_t *row_ptr, uint32_t *col, uint32_t *w, uint32_t *nw, uint64_t *span_len, int *streamed) {
     const size_t n = g_row_ptr.empty() ? 0 : g_row_ptr.size() - 1;

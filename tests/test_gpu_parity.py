@@ -725,3 +725,32 @@ def test_parallel_exact_hub_sums_survive_hostile_inputs(ctx, oracle, oracle_mode
     assert np.array_equal(np.isnan(got), np.isnan(want))
     ok = ~np.isnan(want)
     assert_bit_equal(got[ok], want[ok], "NaN under the hub")
+
+
+def test_group_of_devices_in_one_process(ctx, model_layers):
+    """gvc_group (SURVEY 8(e) behind one call): the forward sharded over several contexts of THIS process,
+    rows exchanged by the stage kernels' peer stores, stages separated by CUDA events.  Two and three
+    shards on one GPU (devices may repeat) and, where a second GPU is visible, two real devices:
+    bit-identical to the one-context forward, odd vertex count (the exact-mode tail vertex), hubs."""
+    cases = [graphs.rmat_graph(13, 16, seed=71, n_limit=8191), graphs.er_graph(5000, 20000, seed=72),
+             _star(40_000, extra=50_000)]
+    layouts = [[0, 0], [0, 0, 0]]
+    if torch.cuda.device_count() >= 2:
+        layouts.append([0, 1])
+    if torch.cuda.device_count() >= 4:
+        layouts.append([0, 1, 2, 3])
+    for devices in layouts:
+        grp = capi.Group(devices)
+        grp.model_upload(model_layers)
+        for g in cases:
+            rp, col, W, NW, x, s = inputs_of(g)
+            ctx.graph_upload(rp, col, W, NW)
+            want = ctx.forward(x, s)
+            want_fast = ctx.forward(x, s, pkg.MODE_FAST)
+            grp.graph_upload(rp, col, W, NW)
+            b = grp.bounds
+            assert b[0] == 0 and b[-1] == g.n and all(b[i] <= b[i + 1] for i in range(len(b) - 1))
+            for _ in range(2):                                   # twice: buffers of the previous forward are reused
+                assert_bit_equal(grp.forward(x, s), want, f"{g.name} on devices {devices}")
+            assert_rel_close(grp.forward(x, s, pkg.MODE_FAST), want_fast, FAST_RTOL, f"{g.name} fast on {devices}")
+        grp.close()

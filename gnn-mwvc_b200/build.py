@@ -36,11 +36,11 @@ def _stale(out: Path, srcs) -> bool:
 
 def build_libgvc(force: bool = False, verbose: bool = False) -> Path:
     out = PKG / "libgvc.so"
-    srcs = [PKG / "csrc" / "gvc_api.cu", PKG / "csrc" / "gvc_kernels.cuh", PKG / "csrc" / "gvc_expf.h",
-            ROOT / "include" / "gvc.h"]
+    srcs = [PKG / "csrc" / "gvc_api.cu", PKG / "csrc" / "gvc_kernels.cuh", PKG / "csrc" / "gvc_px.cuh", PKG / "csrc" / "gvc_expf.h",
+            ROOT / "include" / "gvc.h", PKG / "host" / "gvc_metis.cpp"]
     if force or _stale(out, srcs):
         extra = os.environ.get("GVC_NVCC_EXTRA", "").split()     # e.g. -DGVC_CTAS_PER_SM=2 for experiments
-        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", str(out), str(srcs[0])]
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", str(out), str(srcs[0]), str(srcs[-1])]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

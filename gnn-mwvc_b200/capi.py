@@ -70,6 +70,14 @@ SIGNATURES = {
     "gvc_group_graph_upload": (C.c_int, [C.c_void_p, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
     "gvc_group_bounds": (C.c_int, [C.c_void_p, _u32p]),
     "gvc_group_forward": (C.c_int, [C.c_void_p, _f32p, C.c_float, _f32p, C.c_int]),
+    "gvc_metis_parse": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "gvc_metis_free": (None, [C.c_void_p]),
+    "gvc_metis_vertices": (C.c_uint64, [C.c_void_p]),
+    "gvc_metis_edges": (C.c_uint64, [C.c_void_p]),
+    "gvc_metis_weights": (_u32p, [C.c_void_p]),
+    "gvc_metis_edge_u": (_u32p, [C.c_void_p]),
+    "gvc_metis_edge_v": (_u32p, [C.c_void_p]),
+    "gvc_metis_csr": (C.c_int, [C.c_void_p, _u64p, _u32p, _u32p]),
     "gvc_stream": (C.c_void_p, [C.c_void_p]),
     "gvc_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gvc_sync": (C.c_int, [C.c_void_p]),
@@ -453,6 +461,30 @@ class Group:
         out = np.empty(self.n, np.float32)
         self._check(self.lib.gvc_group_forward(self.h, _ptr(x, _f32p), float(weight_scale), _ptr(out, _f32p), mode))
         return out
+
+
+def parse_metis(path, n_threads: int = 0, csr: bool = False):
+    """gvc_metis_parse: (n, weights u32, eu u32, ev u32[, (row_ptr u64, col u32, nw u32)]) of a METIS file as
+    the reference's parse_graph reads it (src/GNN_VC.cpp:34-91).  Host code, needs no GPU."""
+    lib = load_library()
+    h = C.c_void_p()
+    rc = lib.gvc_metis_parse(str(path).encode(), n_threads, C.byref(h))
+    if rc != 0:
+        raise GvcError(f"libgvc error {rc}: {lib.gvc_last_error().decode()}")
+    try:
+        n, e = int(lib.gvc_metis_vertices(h)), int(lib.gvc_metis_edges(h))
+        w = np.ctypeslib.as_array(lib.gvc_metis_weights(h), shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        eu = np.ctypeslib.as_array(lib.gvc_metis_edge_u(h), shape=(e,)).copy() if e else np.zeros(0, np.uint32)
+        ev = np.ctypeslib.as_array(lib.gvc_metis_edge_v(h), shape=(e,)).copy() if e else np.zeros(0, np.uint32)
+        if not csr:
+            return n, w, eu, ev
+        rp, col, nw = np.zeros(n + 1, np.uint64), np.zeros(max(2 * e, 1), np.uint32), np.zeros(max(n, 1), np.uint32)
+        rc = lib.gvc_metis_csr(h, _ptr(rp, _u64p), _ptr(col, _u32p), _ptr(nw, _u32p))
+        if rc != 0:
+            raise GvcError(f"libgvc error {rc}: {lib.gvc_last_error().decode()}")
+        return n, w, eu, ev, (rp, col[:2 * e], nw[:n])
+    finally:
+        lib.gvc_metis_free(h)
 
 
 def load_model_npz(path):

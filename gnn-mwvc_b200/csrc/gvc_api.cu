@@ -867,6 +867,7 @@ int set_graph_views(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_
 extern "C" {
 
 const char *gvc_last_error(void) { return g_err.c_str(); }
+int gvc_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }   // for the other translation units of libgvc
 int gvc_abi_version(void) { return 3; }
 
 int gvc_ctx_create(gvc_ctx **out, int device) {

@@ -265,6 +265,26 @@ int gvc_sgemm_host(gvc_ctx *ctx, int trans_a, int trans_b, uint64_t m, uint64_t 
                    const float *A, uint64_t lda, const float *B, uint64_t ldb, float beta, float *C,
                    uint64_t ldc);
 
+/* ---- the METIS-format reader: parse_graph (src/GNN_VC.cpp:34-91; format README.md:45-60) ------------
+ * SURVEY.md 8(f) item 3.  The reference reads its input with one getline + stringstream per vertex;
+ * this reader maps the file and parses it with n_threads threads (0 = all cores), with the same
+ * result: the vertex weights and the sorted, de-duplicated undirected edges (u < v) that parse_graph
+ * hands to the reduction_graph constructor -- including its quirks (only neighbours with a larger id
+ * are kept; a header E larger than the file's edge count leaves one (0,0) self-loop; see
+ * host/gvc_metis.cpp).  Where the reference would run into undefined behaviour (more edges than the
+ * header says, ids out of range) an error is returned instead.  gvc_metis_csr builds the adjacency
+ * exactly as the reduction_graph constructor does (include/reduction_graph.hpp:103-128), ready for
+ * gvc_graph_upload.  Pure host code. */
+typedef struct gvc_metis gvc_metis;
+int gvc_metis_parse(const char *path, int n_threads, gvc_metis **out);
+void gvc_metis_free(gvc_metis *m);
+uint64_t gvc_metis_vertices(const gvc_metis *m);
+uint64_t gvc_metis_edges(const gvc_metis *m);
+const uint32_t *gvc_metis_weights(const gvc_metis *m);
+const uint32_t *gvc_metis_edge_u(const gvc_metis *m);
+const uint32_t *gvc_metis_edge_v(const gvc_metis *m);
+int gvc_metis_csr(const gvc_metis *m, uint64_t *row_ptr, uint32_t *col, uint32_t *nw);
+
 /* ---- plumbing ----------------------------------------------------------- */
 
 /* The context's CUDA stream as an opaque handle (cudaStream_t). */

@@ -227,6 +227,8 @@ class Reference:
         L.ref_sigmoid.argtypes = [C.c_size_t, _f32p, _f32p]
         L.ref_linear_init.argtypes = [C.c_int, C.c_int, C.c_size_t, _f32p]
         L.ref_dot.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, _f32p, _f32p, C.c_float, _f32p]
+        if hasattr(L, "ref_parse_graph"):          # only in the build over the reference's sources
+            L.ref_parse_graph.argtypes = [C.c_char_p, _u64p, _u64p, _u32p, _u32p, _u32p]
         L.ref_graph_create.restype = C.c_void_p
         L.ref_graph_create.argtypes = [C.c_uint32, C.c_uint64, _u32p, _u32p, _u32p]
         L.ref_graph_destroy.argtypes = [C.c_void_p]
@@ -349,6 +351,15 @@ class Reference:
         assert rc == 0 or n == 0, "predict returned an unexpected shape"
         self.last_seconds = sec.value
         return out
+
+    def parse_graph(self, path):
+        """The reference's own parse_graph (src/GNN_VC.cpp:34-91): (n, weights, eu, ev)."""
+        n, e = C.c_uint64(), C.c_uint64()
+        self.L.ref_parse_graph(str(path).encode(), C.byref(n), C.byref(e), None, None, None)
+        w = np.zeros(max(n.value, 1), np.uint32)
+        eu, ev = np.zeros(max(e.value, 1), np.uint32), np.zeros(max(e.value, 1), np.uint32)
+        self.L.ref_parse_graph(str(path).encode(), None, None, _p(w, _u32p), _p(eu, _u32p), _p(ev, _u32p))
+        return int(n.value), w[:n.value], eu[:e.value], ev[:e.value]
 
     def selection_order(self, h, gh, x, scale):
         """(scores, nodes): predict and the driver's sort of the vertices (src/GNN_VC.cpp:186-206)."""

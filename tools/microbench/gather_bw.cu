@@ -101,8 +101,10 @@ __global__ void gather_cpasync(const float4* __restrict__ table, const unsigned*
 }
 
 int main(int argc, char** argv) {
-    const size_t n = 1 << 20;
+    // GATHER_ROWS=8388608: a 512 MB table, four times the L2 -- the regime of the 100 M-edge graph (R-MAT scale 23)
+    const size_t n = getenv("GATHER_ROWS") ? (size_t)atoll(getenv("GATHER_ROWS")) : (size_t)1 << 20;
     size_t m = 32u << 20;
+    printf("table: %zu rows of 64 B = %.0f MB\n", n, n * 64.0 / 1e6);
     std::vector<unsigned> h(m);
     unsigned s = 12345;
     for (size_t i = 0; i < m; ++i) { s = s * 1664525u + 1013904223u; h[i] = (s >> 8) % n; }

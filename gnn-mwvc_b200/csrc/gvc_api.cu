@@ -151,6 +151,7 @@ struct gvc_ctx {
     std::vector<HostLayer> layers;
     bool fused = false;
     float *d_stage_params[3] = {nullptr, nullptr, nullptr};
+    float *d_stage_params_fast[3] = {nullptr, nullptr, nullptr};     // fragment-ordered TF32 hi/lo weights (fast mode on the tensor cores)
     std::vector<float> layer_scales;     // gvc_model_weight_scales: WEIGHT_SCALE of every graph layer (empty: the call's scalar)
 
     // graph shard
@@ -244,6 +245,47 @@ std::vector<float> pack_stage(const std::vector<HostLayer> &L, int stage) {
     for (int j = 0; j < 3; ++j) {
         const HostLayer *l = lin[stage * 3 + j];
         out.insert(out.end(), l->W.begin(), l->W.begin() + (size_t)K[j] * N[j]);   // first K rows (drops 32..34 of 35)
+        out.insert(out.end(), l->b.begin(), l->b.begin() + N[j]);
+    }
+    return out;
+}
+
+// The fast mode's parameter block of one stage: weights in mma fragment order, split into TF32 hi / lo
+// (gvc_kernels.cuh stage_mma_floats).
+float tf32_rna(float x) {                       // cvt.rna.tf32.f32: 10 mantissa bits, ties away from zero
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+std::vector<float> pack_stage_mma(const std::vector<HostLayer> &L, int stage) {
+    std::vector<const HostLayer *> lin;
+    for (auto &l : L) if (l.kind == GVC_LINEAR) lin.push_back(&l);
+    const StageDims D = stage_dims(stage);
+    const int K[3] = {D.Ka, D.Kb, D.Kc}, N[3] = {D.Na, D.Nb, D.Nc};
+    std::vector<float> out;
+    for (int j = 0; j < 3; ++j) {
+        const HostLayer *l = lin[stage * 3 + j];
+        auto w = [&](int k, int n) { return k < K[j] ? l->W[(size_t)k * N[j] + n] : 0.0f; };   // rows 32..34 of the 35-row matrices are dead
+        if (N[j] >= 8) {
+            const int KB = (K[j] + 7) / 8, NB = N[j] / 8;
+            for (int kb = 0; kb < KB; ++kb)
+                for (int nb = 0; nb < NB; ++nb) {
+                    float blk[128];
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int kk = 8 * kb + lane % 4, nn = 8 * nb + lane / 4;
+                        const float b0 = w(kk, nn), b1 = w(kk + 4, nn);
+                        const float h0 = tf32_rna(b0), h1 = tf32_rna(b1);
+                        blk[lane] = h0; blk[32 + lane] = h1;
+                        blk[64 + lane] = tf32_rna(b0 - h0); blk[96 + lane] = tf32_rna(b1 - h1);
+                    }
+                    out.insert(out.end(), blk, blk + 128);
+                }
+        } else {
+            out.insert(out.end(), l->W.begin(), l->W.begin() + (size_t)K[j] * N[j]);
+        }
         out.insert(out.end(), l->b.begin(), l->b.begin() + N[j]);
     }
     return out;
@@ -415,7 +457,7 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     const unsigned grid = std::max(1u, std::min<unsigned>(c->ctas_per_sm[STAGE] * c->num_sms, want));
     Schedule sc_launch = sc;
     sc_launch.n_ring_ctas = std::min<unsigned>(grid, (unsigned)c->num_sms);   // one ring CTA per SM at most
-    const size_t smem = stage_smem_bytes<STAGE>();
+    const size_t smem = exact ? stage_smem_bytes<STAGE, true>() : stage_smem_bytes<STAGE, false>();
     // task counter + per-feature-tile completion counters start at zero
     PeerOut peers{};
     if (STAGE < 2) peers = c->peers[STAGE];
@@ -452,7 +494,7 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     const uint4 *a_vrec = c->d_vrec.p;
     float *a_feat = c->d_feat.p;
     uint32_t *a_sync = c->d_sync.p;
-    const float *a_params = c->d_stage_params[STAGE];
+    const float *a_params = (exact || !GVC_FAST_MMA) ? c->d_stage_params[STAGE] : c->d_stage_params_fast[STAGE];
     const uint32_t a_vb = c->v_begin;
     if (mode == GVC_MODE_EXACT) {
         GVC_CUDA(cudaLaunchKernelEx(&cfg, stage_kernel<STAGE, true>, a_rp, a_col, a_w, a_nw, a_order, a_vrec, sc_launch, hub, px, peers,
@@ -752,12 +794,12 @@ int ensure_ring(gvc_ctx *c, int n_slots, size_t slot_bytes) {
 
 template <int STAGE>
 int set_stage_attrs(gvc_ctx *c) {
-    const int smem = (int)stage_smem_bytes<STAGE>();
+    const int smem = (int)stage_smem_bytes<STAGE, true>(), smem_fast = (int)stage_smem_bytes<STAGE, false>();
     GVC_CUDA(cudaFuncSetAttribute(stage_kernel<STAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    GVC_CUDA(cudaFuncSetAttribute(stage_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GVC_CUDA(cudaFuncSetAttribute(stage_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fast));
     int a = 0, b = 0;
     GVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, stage_kernel<STAGE, true>, kCtaThreads, smem));
-    GVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage_kernel<STAGE, false>, kCtaThreads, smem));
+    GVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, stage_kernel<STAGE, false>, kCtaThreads, smem_fast));
     c->ctas_per_sm[STAGE] = std::max(1, std::min(kCtasPerSm, std::min(a, b)));
     return 0;
 }
@@ -914,6 +956,7 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     cudaStreamSynchronize(c->copy_stream);
     for (auto &l : c->layers) { if (l.dW) cudaFree(l.dW); if (l.db) cudaFree(l.db); }
     for (auto &p : c->d_stage_params) if (p) cudaFree(p);
+    for (auto &p : c->d_stage_params_fast) if (p) cudaFree(p);
     c->own_row_ptr.release(); c->own_col.release(); c->own_W.release(); c->own_NW.release();
     c->d_row_ptr64.release(); c->d_flag.release();
     c->d_span.release(); c->d_rb.release(); c->d_re.release(); c->d_blk.release();
@@ -958,6 +1001,7 @@ int gvc_model_upload(gvc_ctx *c, int n_layers, const int *kinds, const int *rows
         for (auto &l : c->layers) { if (l.dW) cudaFree(l.dW); if (l.db) cudaFree(l.db); }
         c->layers.clear();
         for (auto &p : c->d_stage_params) { if (p) cudaFree(p); p = nullptr; }
+        for (auto &p : c->d_stage_params_fast) { if (p) cudaFree(p); p = nullptr; }
         c->fused = false;
         c->layer_scales.clear();
     };
@@ -981,6 +1025,9 @@ int gvc_model_upload(gvc_ctx *c, int n_layers, const int *kinds, const int *rows
                 std::vector<float> p = pack_stage(c->layers, s);
                 GVC_CUDA(cudaMalloc(&c->d_stage_params[s], p.size() * sizeof(float)));
                 GVC_CUDA(cudaMemcpy(c->d_stage_params[s], p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+                std::vector<float> pf = pack_stage_mma(c->layers, s);
+                GVC_CUDA(cudaMalloc(&c->d_stage_params_fast[s], pf.size() * sizeof(float)));
+                GVC_CUDA(cudaMemcpy(c->d_stage_params_fast[s], pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice));
             }
         }
         GVC_CUDA(cudaStreamSynchronize(c->stream));

@@ -195,6 +195,26 @@ __host__ __device__ constexpr StageDims stage_dims(int stage) {
 }
 __host__ __device__ constexpr int stage_feat_width(int stage) { return stage == 0 ? 5 : 32; }
 
+// Fast mode runs the [32 x K] . [K x N] layers on the tensor cores (mma.sync m16n8k8, TF32 inputs, fp32
+// accumulation, every product split 3 ways -- hi.hi + lo.hi + hi.lo -- so that the result keeps fp32
+// accuracy: ~1e-6 against the 1e-4 the fast mode promises).  Its parameter block holds the weights in
+// FRAGMENT order, already split into TF32 hi and lo parts: for every (k block of 8, n block of 8) 128
+// floats [hi b0 x 32 lanes][hi b1][lo b0][lo b1], b0 = W[8 kb + lane % 4][8 nb + lane / 4], b1 four rows
+// further down (rows past K are zero); then the bias.  The 16 -> 1 layer of stage 2 stays scalar.
+#ifndef GVC_FAST_MMA
+#define GVC_FAST_MMA 1
+#endif
+__host__ __device__ constexpr int mma_layer_floats(int K, int N) { return ((K + 7) / 8) * (N / 8) * 128; }
+__host__ __device__ constexpr int stage_mma_floats(int stage) {
+    const StageDims D = stage_dims(stage);
+    return mma_layer_floats(D.Ka, D.Na) + D.Na + mma_layer_floats(D.Kb, D.Nb) + D.Nb +
+           (D.Nc >= 8 ? mma_layer_floats(D.Kc, D.Nc) : D.Kc * D.Nc) + D.Nc;
+}
+template <int STAGE, bool EXACT>
+__host__ __device__ constexpr int stage_param_floats() {
+    return (EXACT || !GVC_FAST_MMA) ? stage_dims(STAGE).floats() : stage_mma_floats(STAGE);
+}
+
 __device__ __forceinline__ float relu_ref(float v) { return v < 0.0f ? 0.0f : v; }   // std::max(x, 0.0f), :46
 
 template <bool EXACT>
@@ -309,6 +329,116 @@ __device__ __forceinline__ void tile_linear_relu_store16(const float *__restrict
     }
 }
 
+// ---- fast mode: the same layers on the tensor cores -------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// acc[mb][nb][.] = sum over k of T[k][vertex] * W[k][n] for the 32 vertices of the tile: two 16-vertex
+// row blocks (mb), NOUT / 8 column blocks (nb).  Fragment coordinates of lane l (r = l / 4, c = l % 4):
+// A a0 (r, c) a1 (r + 8, c) a2 (r, c + 4) a3 (r + 8, c + 4);  B b0 (c, r) b1 (c + 4, r);
+// C c0 (r, 2c) c1 (r, 2c + 1) c2 (r + 8, 2c) c3 (r + 8, 2c + 1).
+template <int K, int NOUT>
+__device__ __forceinline__ void tile_mma(const float *__restrict__ T, const float *__restrict__ Wf, int lane,
+                                         float (&acc)[2][NOUT / 8][4]) {
+    constexpr int KB = (K + 7) / 8, NB = NOUT / 8;
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mb][nb][i] = 0.0f;
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+        uint32_t hi[2][4], lo[2][4];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            const float *t = T + (8 * kb + c) * kTileStride + 16 * mb + r;
+            const float a[4] = {t[0], t[8], t[4 * kTileStride], t[4 * kTileStride + 8]};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                hi[mb][i] = to_tf32(a[i]);
+                lo[mb][i] = to_tf32(a[i] - __uint_as_float(hi[mb][i]));
+            }
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            const float *f = Wf + (kb * NB + nb) * 128 + lane;
+            const uint32_t bh0 = __float_as_uint(f[0]), bh1 = __float_as_uint(f[32]);
+            const uint32_t bl0 = __float_as_uint(f[64]), bl1 = __float_as_uint(f[96]);
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                mma_tf32(acc[mb][nb], lo[mb], bh0, bh1);     // the small terms first
+                mma_tf32(acc[mb][nb], hi[mb], bl0, bl1);
+                mma_tf32(acc[mb][nb], hi[mb], bh0, bh1);
+            }
+        }
+    }
+}
+
+// one layer + bias + ReLU over the warp's tile, in place
+template <int K, int NOUT>
+__device__ __forceinline__ void tile_linear_relu_mma(float *__restrict__ T, const float *__restrict__ Wf,
+                                                     const float *__restrict__ bsm, int lane) {
+    float acc[2][NOUT / 8][4];
+    tile_mma<K, NOUT>(T, Wf, lane, acc);
+    __syncwarp();   // every lane is done reading the input tile
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int nb = 0; nb < NOUT / 8; ++nb) {
+        const float b0 = bsm[8 * nb + 2 * c], b1 = bsm[8 * nb + 2 * c + 1];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            float *t = T + (8 * nb + 2 * c) * kTileStride + 16 * mb + r;
+            t[0] = relu_ref(acc[mb][nb][0] + b0);
+            t[kTileStride] = relu_ref(acc[mb][nb][1] + b1);
+            t[8] = relu_ref(acc[mb][nb][2] + b0);
+            t[kTileStride + 8] = relu_ref(acc[mb][nb][3] + b1);
+        }
+    }
+    __syncwarp();
+}
+
+// last layer of stages 0/1 (K = 32 -> 16) + bias + ReLU, stored straight from the accumulator fragments
+template <int K>
+__device__ __forceinline__ void tile_linear_relu_store16_mma(const float *__restrict__ T, const float *__restrict__ Wf,
+                                                             const float *__restrict__ bsm, int lane, float *__restrict__ out,
+                                                             const uint32_t *__restrict__ vid, int valid, const PeerOut &peers,
+                                                             int live) {
+    float acc[2][2][4];
+    tile_mma<K, 16>(T, Wf, lane, acc);
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                                  // rows r and r + 8 of the block
+            const int i = 16 * mb + 8 * h + r;
+            if (i < valid) {
+                const uint32_t v = vid[i];
+                const uint32_t m = (i < live) ? (peers.mask ? peers.mask[v] : 0xFFu) : 0u;
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    float2 o;
+                    o.x = relu_ref(acc[mb][nb][2 * h] + bsm[8 * nb + 2 * c]);
+                    o.y = relu_ref(acc[mb][nb][2 * h + 1] + bsm[8 * nb + 2 * c + 1]);
+                    const size_t at = (size_t)v * 16 + 8 * nb + 2 * c;
+                    *reinterpret_cast<float2 *>(out + at) = o;
+#pragma unroll 1
+                    for (int q = 0; q < peers.n; ++q)
+                        if (m >> q & 1u) *reinterpret_cast<float2 *>(peers.p[q] + at) = o;
+                }
+            }
+        }
+}
+
 // sigmoid::forward :49-52
 template <bool EXACT>
 __device__ __forceinline__ float sigmoid_ref(float v) {
@@ -330,6 +460,34 @@ __device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const u
     if (lane < count) out[(size_t)(vid[lane] - (STAGE < 2 ? 0u : v_begin)) * (STAGE < 2 ? 16 : 1)] = T[lane];
     return;
 #endif
+    if constexpr (!EXACT && GVC_FAST_MMA) {
+        // fragment-ordered parameter block (see stage_mma_floats)
+        const float *Fa = P, *fa = Fa + mma_layer_floats(D.Ka, D.Na);
+        const float *Fb = fa + D.Na, *fb = Fb + mma_layer_floats(D.Kb, D.Nb);
+        const float *Fc = fb + D.Nb;
+        if constexpr (D.Ka % 8 != 0) {          // stage 0: features 5..7 of the first k block must be finite zeros
+#pragma unroll
+            for (int k = D.Ka; k < (D.Ka + 7) / 8 * 8; ++k) T[k * kTileStride + lane] = 0.0f;
+            __syncwarp();
+        }
+        tile_linear_relu_mma<D.Ka, D.Na>(T, Fa, fa, lane);
+        tile_linear_relu_mma<D.Kb, D.Nb>(T, Fb, fb, lane);
+        if constexpr (STAGE < 2) {
+            tile_linear_relu_store16_mma<D.Kc>(T, Fc, Fc + mma_layer_floats(D.Kc, D.Nc), lane, out, vid, count, peers, live);
+        } else {
+            const float *Wc1 = Fc, *bc1 = Fc + D.Kc * D.Nc;
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s = fmaf(T[k * kTileStride + lane], Wc1[k], s);
+            if (lane < count) {
+                const float sg = sigmoid_ref<false>(s + bc1[0]);
+                out[vid[lane] - v_begin] = sg;
+                store_selection_key(peers, vid[lane] - v_begin, sg);
+            }
+        }
+        __syncwarp();
+        return;
+    }
     tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane);
     tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane);
     if constexpr (STAGE < 2) {
@@ -927,13 +1085,14 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     constexpr StageDims D = stage_dims(STAGE);
     extern __shared__ __align__(16) float smem[];
     float *P = smem;                                             // packed parameters
-    constexpr int kParamFloats = (D.floats() + 3) / 4 * 4;
+    constexpr int kParams = stage_param_floats<STAGE, EXACT>();
+    constexpr int kParamFloats = (kParams + 3) / 4 * 4;
     float *ring_acc = smem + kParamFloats;                       // 16 sums, the CTA's ring claim [16], a chunk record [20..23],
     PeerOut &peers = *reinterpret_cast<PeerOut *>(ring_acc + 24);   // the peer table [24..47] (shared memory: passed by reference)
     static_assert(sizeof(PeerOut) <= 96, "PeerOut is laid out in 24 floats of shared memory");
     float *warp_mem = ring_acc + 48;
 
-    for (int i = threadIdx.x; i < D.floats(); i += kCtaThreads) P[i] = __ldg(params + i);
+    for (int i = threadIdx.x; i < kParams; i += kCtaThreads) P[i] = __ldg(params + i);
     if (threadIdx.x == 0) peers = peers_arg;
     __syncthreads();
 
@@ -1145,10 +1304,9 @@ stage_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ 
     }
 }
 
-template <int STAGE>
+template <int STAGE, bool EXACT>
 constexpr size_t stage_smem_bytes() {
-    constexpr StageDims D = stage_dims(STAGE);
-    return ((D.floats() + 3) / 4 * 4 + 48 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
+    return ((stage_param_floats<STAGE, EXACT>() + 3) / 4 * 4 + 48 + kWarpsPerCta * kWarpSmemFloats) * sizeof(float);
 }
 
 // ---- schedule construction (graph upload time) -------------------------------------------

@@ -416,27 +416,32 @@ __device__ __forceinline__ void tile_linear_relu_store16_mma(const float *__rest
     float acc[2][2][4];
     tile_mma<K, 16>(T, Wf, lane, acc);
     const int r = lane >> 2, c = lane & 3;
+    // A lane holds outputs (2c, 2c + 1) of rows r and r + 8; it trades one of the pairs with its neighbour
+    // (lane ^ 1) so that even lanes end up with four consecutive outputs of row r and odd lanes with four of
+    // row r + 8: 128-bit stores, to the local buffer and over NVLink alike.
 #pragma unroll
-    for (int mb = 0; mb < 2; ++mb)
+    for (int mb = 0; mb < 2; ++mb) {
+        const int i = 16 * mb + r + ((c & 1) ? 8 : 0);
+        const bool on = i < valid;
+        const uint32_t v = on ? vid[i] : 0u;
+        const uint32_t m = (on && i < live) ? (peers.mask ? peers.mask[v] : 0xFFu) : 0u;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {                                  // rows r and r + 8 of the block
-            const int i = 16 * mb + 8 * h + r;
-            if (i < valid) {
-                const uint32_t v = vid[i];
-                const uint32_t m = (i < live) ? (peers.mask ? peers.mask[v] : 0xFFu) : 0u;
-#pragma unroll
-                for (int nb = 0; nb < 2; ++nb) {
-                    float2 o;
-                    o.x = relu_ref(acc[mb][nb][2 * h] + bsm[8 * nb + 2 * c]);
-                    o.y = relu_ref(acc[mb][nb][2 * h + 1] + bsm[8 * nb + 2 * c + 1]);
-                    const size_t at = (size_t)v * 16 + 8 * nb + 2 * c;
-                    *reinterpret_cast<float2 *>(out + at) = o;
+        for (int nb = 0; nb < 2; ++nb) {
+            const float b0 = bsm[8 * nb + 2 * c], b1 = bsm[8 * nb + 2 * c + 1];
+            const float lo0 = relu_ref(acc[mb][nb][0] + b0), lo1 = relu_ref(acc[mb][nb][1] + b1);     // row r
+            const float hi0 = relu_ref(acc[mb][nb][2] + b0), hi1 = relu_ref(acc[mb][nb][3] + b1);     // row r + 8
+            const float sx = (c & 1) ? lo0 : hi0, sy = (c & 1) ? lo1 : hi1;                          // what the neighbour wants
+            const float gx = __shfl_xor_sync(0xffffffffu, sx, 1), gy = __shfl_xor_sync(0xffffffffu, sy, 1);
+            const float4 o = (c & 1) ? make_float4(gx, gy, hi0, hi1) : make_float4(lo0, lo1, gx, gy);
+            if (on) {
+                const size_t at = (size_t)v * 16 + 8 * nb + 4 * (c >> 1);
+                *reinterpret_cast<float4 *>(out + at) = o;
 #pragma unroll 1
-                    for (int q = 0; q < peers.n; ++q)
-                        if (m >> q & 1u) *reinterpret_cast<float2 *>(peers.p[q] + at) = o;
-                }
+                for (int q = 0; q < peers.n; ++q)
+                    if (m >> q & 1u) *reinterpret_cast<float4 *>(peers.p[q] + at) = o;
             }
         }
+    }
 }
 
 // sigmoid::forward :49-52

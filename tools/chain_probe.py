@@ -3,7 +3,7 @@
 leaves) leave nothing else to do, so the stage time is the hub's chain: ns per neighbour, exact and
 fast mode, for every stage.  With `busy` > 0 the graph also gets `busy` vertices of degree 32 that
 keep the other warps of the GPU occupied while the chain runs.
-usage: python tools/chain_probe.py [D=262144] [busy=0]"""
+usage: python tools/chain_probe.py [D=262144 | rmatSCALE] [busy=0]"""
 import json
 import os
 import sys
@@ -17,7 +17,8 @@ sys.path.insert(0, str(ROOT))
 import gnn_mwvc_b200 as pkg  # noqa: E402
 from gnn_mwvc_b200 import capi, graphs  # noqa: E402
 
-D = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+RMAT = len(sys.argv) > 1 and sys.argv[1].startswith("rmat")      # "rmat20": the bench graph instead of a star
+D = 262144 if RMAT or len(sys.argv) < 2 else int(sys.argv[1])
 busy = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 dev = torch.device("cuda:0")
 n = 1 + D + busy
@@ -30,6 +31,10 @@ if busy:
     eu.append(b0 + src); ev.append(b0 + dst)
 a, b = graphs._canonical_edges(torch.cat(eu).to(dev), torch.cat(ev).to(dev), n)
 g = graphs.graph_from_edges(n, a, b, graphs.random_weights(n, 5, dev), name="star")
+if RMAT:
+    g = graphs.rmat_graph(int(sys.argv[1][4:]), 16, seed=42, device=dev)
+    n = g.n
+    D = int((g.row_ptr[1:] - g.row_ptr[:-1]).max())
 ctx = pkg.Context(0)
 ctx.model_upload(capi.load_model_npz(ROOT / "tests" / "golden" / "mwvc_model.npz"))
 ctx.graph_adopt(g.row_ptr.to(torch.int32).contiguous(), g.col, g.weights, g.nw)

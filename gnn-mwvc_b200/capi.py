@@ -38,6 +38,7 @@ SIGNATURES = {
     "gvc_graph_staging": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(_u64p), C.POINTER(_u32p),
                                     C.POINTER(_u32p), C.POINTER(_u32p)]),
     "gvc_graph_upload_stream": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "gvc_graph_upload_stream_x": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gvc_graph_adopt_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gvc_graph_set_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "gvc_peer_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
@@ -204,10 +205,11 @@ class Context:
                                                     _ptr(col, _u32p), _ptr(W, _u32p), _ptr(NW, _u32p)))
         self.n_global, self.v_begin, self.v_end = n_global, v_begin, v_end
 
-    def graph_upload_ranges(self, span, begin, end, W, NW, n_threads: int = 0):
-        """gvc_graph_upload_stream from numpy arrays: `span` is the raw edge array (holes allowed),
+    def graph_upload_ranges(self, span, begin, end, W, NW, n_threads: int = 0, x=None):
+        """gvc_graph_upload_stream(_x) from numpy arrays: `span` is the raw edge array (holes allowed),
         begin/end the per-vertex ranges into it.  The callbacks copy slices into libgvc's pinned slots
-        (possibly from several of its worker threads)."""
+        (possibly from several of its worker threads).  With `x` the forward's input travels along
+        (then ``forward(None, ...)`` uses it)."""
         span = _np(span, np.uint32)
         begin, end = _np(begin, np.uint32), _np(end, np.uint32)
         W, NW = _np(W, np.uint32), _np(NW, np.uint32)
@@ -222,8 +224,15 @@ class Context:
         def fill_span(_user, offset, count, dst):
             np.ctypeslib.as_array(dst, shape=(count,))[:] = span[offset:offset + count]
         fv, fs = FV(fill_vertices), FS(fill_span)
-        self._check(self.lib.gvc_graph_upload_stream(self.h, n, len(span), C.cast(fv, C.c_void_p), C.cast(fs, C.c_void_p),
-                                                     None, n_threads))
+        if x is None:
+            self._check(self.lib.gvc_graph_upload_stream(self.h, n, len(span), C.cast(fv, C.c_void_p), C.cast(fs, C.c_void_p),
+                                                         None, n_threads))
+        else:
+            x = _np(x, np.float32).ravel()
+            if x.size != n:
+                raise GvcError(f"x has {x.size} entries, the graph {n} vertices")
+            self._check(self.lib.gvc_graph_upload_stream_x(self.h, n, len(span), C.cast(fv, C.c_void_p), C.cast(fs, C.c_void_p),
+                                                           None, n_threads, _ptr(x, _f32p)))
         self.n_global, self.v_begin, self.v_end = n, 0, n
 
     def graph_staging(self, n_local: int, nnz: int):
@@ -292,11 +301,15 @@ class Context:
 
     # -- forward ---------------------------------------------------------------
     def forward(self, x, weight_scale: float, mode: int = MODE_EXACT) -> np.ndarray:
-        """Host in, host out: gnn::model::predict."""
+        """Host in, host out: gnn::model::predict.  x = None: the input that came with the graph
+        (graph_upload_ranges(..., x=...))."""
+        out = np.empty(self.n_global, np.float32)
+        if x is None:
+            self._check(self.lib.gvc_forward(self.h, None, float(weight_scale), _ptr(out, _f32p), mode))
+            return out
         x = _np(x, np.float32).ravel()
         if x.size != self.n_global:
             raise GvcError(f"x has {x.size} entries, graph has {self.n_global} vertices")
-        out = np.empty(self.n_global, np.float32)
         self._check(self.lib.gvc_forward(self.h, _ptr(x, _f32p), float(weight_scale), _ptr(out, _f32p), mode))
         return out
 

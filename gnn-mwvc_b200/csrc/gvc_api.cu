@@ -176,7 +176,7 @@ struct gvc_ctx {
     DevBuf<uint32_t> d_span, d_rb, d_re; // raw edge span, per-vertex [begin, end) into it
     DevBuf<uint64_t> d_blk;              // block sums of the degree scan (+ the total at the end)
     cudaStream_t copy_stream = nullptr;  // the adjacency travels here while the schedule is built on `stream`
-    cudaEvent_t ev_begin = nullptr, ev_copy = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_copy = nullptr, ev_vert = nullptr;
     // schedule (gvc_kernels.cuh): vertices counting-sorted by degree bin + tile classes
     DevBuf<uint32_t> d_order, d_bins, d_sync;
     DevBuf<uint4> d_vrec;
@@ -203,6 +203,7 @@ struct gvc_ctx {
     DevBuf<float> d_x, d_h1, d_h2, d_scores, d_ping, d_pong;
     DevBuf<float> d_keys;                // selection keys of the last forward (gvc_forward_keys)
     DevBuf<uint8_t> d_side;
+    uint32_t x_resident_n = 0;           // gvc_graph_upload_stream_x left the input of this many vertices in d_x (gvc_forward with x = NULL)
     uint32_t keys_valid_n = 0;           // d_keys/d_side hold the keys of the last gvc_forward for this many vertices
     float *keys_out = nullptr;           // where stage 2 of the NEXT launch writes them (null: not wanted)
     uint8_t *side_out = nullptr;
@@ -897,6 +898,7 @@ int set_graph_views(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint32_t v_
     c->row_ptr = rp; c->col = col; c->Wv = W; c->NWv = NW;
     c->have_graph = true;
     c->keys_valid_n = 0;
+    c->x_resident_n = 0;
     c->tail_override = -1;
     int rc;
     if ((rc = ensure_activations(c))) return rc;
@@ -935,11 +937,13 @@ int gvc_ctx_create(gvc_ctx **out, int device) {
     int rc = 0;
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c->ev_begin, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming)) != cudaSuccess)
+        (e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->ev_vert, cudaEventDisableTiming)) != cudaSuccess)
         rc = fail(1000 + (int)e, "copy stream/events: %s", cudaGetErrorString(e));
     if (rc || (rc = set_stage_attrs<0>(c)) || (rc = set_stage_attrs<1>(c)) || (rc = set_stage_attrs<2>(c))) {
         if (c->ev_begin) cudaEventDestroy(c->ev_begin);
         if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+        if (c->ev_vert) cudaEventDestroy(c->ev_vert);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         cudaStreamDestroy(c->own_stream);
         delete c;
@@ -976,6 +980,7 @@ void gvc_ctx_destroy(gvc_ctx *c) {
     tl_arena = nullptr;
     cudaEventDestroy(c->ev_begin);
     cudaEventDestroy(c->ev_copy);
+    cudaEventDestroy(c->ev_vert);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -1133,8 +1138,8 @@ int gvc_graph_upload_shard(gvc_ctx *c, uint32_t n_global, uint32_t v_begin, uint
     return 0;
 }
 
-int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_vertices_fn fill_vertices,
-                            gvc_fill_span_fn fill_span, void *user, int n_threads) {
+int gvc_graph_upload_stream_x(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_vertices_fn fill_vertices,
+                              gvc_fill_span_fn fill_span, void *user, int n_threads, const float *x) {
     int rc;
     if ((rc = check_ctx(c))) return rc;
     if (n && !fill_vertices) return fail(GVC_ERR_ARG, "null vertex callback");
@@ -1143,22 +1148,32 @@ int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_
     if ((rc = use_device(c))) return rc;
     Tracer tr;
     c->have_graph = false;
-    // work items: vertex chunks (4 arrays of kVChunk uint32 = one slot) and span chunks (one slot each)
-    constexpr uint32_t kVChunk = 16384;                  // 4 x 64 KB
-    constexpr size_t kSlotBytes = 4 * (size_t)kVChunk * sizeof(uint32_t);      // 256 KB
-    constexpr uint64_t kSChunk = kSlotBytes / sizeof(uint32_t);
-    const uint64_t n_vchunks = ((uint64_t)n + kVChunk - 1) / kVChunk, n_schunks = (span_len + kSChunk - 1) / kSChunk;
+    c->x_resident_n = 0;
+    // Work items: vertex chunks (begin, end, W, NW and -- when x travels along -- x: 5 arrays of v_chunk
+    // words in one slot) and span chunks (one slot each).  Every item costs two or more driver calls
+    // (copy + event), and those serialise over all threads: measured at 256 KB per slot on the 146 MB
+    // benchmark graph, 544 items kept the copy engine at half of the PCIe rate.  Large graphs therefore
+    // use 1 MB slots, small ones 256 KB (more pieces to overlap filling with copying).
+    static const size_t env_slot_kb = [] { const char *e = std::getenv("GVC_SLOT_KB"); return e ? (size_t)std::strtoull(e, nullptr, 10) : 0; }();
+    const uint64_t total_bytes = 20ull * n + 4ull * span_len;
+    size_t slot_bytes = env_slot_kb ? (env_slot_kb << 10) : total_bytes >= (32ull << 20) ? ((size_t)1 << 20) : ((size_t)256 << 10);
+    slot_bytes = std::max<size_t>(64u << 10, (slot_bytes + 4095) & ~(size_t)4095);
+    slot_bytes = std::max(slot_bytes, c->slot_bytes);            // an existing ring is never shrunk
+    const uint32_t v_chunk = (uint32_t)(slot_bytes / 20 / 1024 * 1024);           // 5 arrays per slot
+    const uint64_t s_chunk = slot_bytes / sizeof(uint32_t);
+    const uint64_t n_vchunks = ((uint64_t)n + v_chunk - 1) / v_chunk, n_schunks = (span_len + s_chunk - 1) / s_chunk;
     const uint64_t n_items = n_vchunks + n_schunks;
     static const int env_threads = [] { const char *e = std::getenv("GVC_UPLOAD_THREADS"); return e ? std::atoi(e) : 0; }();
     int workers = n_threads > 0 ? n_threads : env_threads > 0 ? env_threads
                                 : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
     workers = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)workers, (n_items + 3) / 4));   // >= 4 items per thread
-    if ((rc = ensure_ring(c, std::max(2 * workers, 16) / workers * workers, kSlotBytes))) return rc;
+    if ((rc = ensure_ring(c, std::max(2 * workers, 16) / workers * workers, slot_bytes))) return rc;
     arena_hint(c, n, span_len);
     if ((rc = c->d_rb.reserve(n))) return rc;
     if ((rc = c->d_re.reserve(n))) return rc;
     if ((rc = c->own_W.reserve(n))) return rc;
     if ((rc = c->own_NW.reserve(n))) return rc;
+    if (x && (rc = c->d_x.reserve(n))) return rc;
     if ((rc = c->own_row_ptr.reserve((size_t)n + 1))) return rc;
     if ((rc = c->d_span.reserve(span_len + 4))) return rc;
     if ((rc = c->own_col.reserve(span_len + 4))) return rc;      // nnz <= span_len once the ranges are known good
@@ -1171,7 +1186,7 @@ int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_
     GVC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_begin, 0));
 
     // ---- host side: workers fill slots through the callbacks and send them off ------------------
-    std::atomic<uint64_t> next{0};
+    std::atomic<uint64_t> next{0}, v_issued{0};
     std::atomic<int> err{0};
     std::atomic<uint64_t> ns_wait{0}, ns_fill{0}, ns_issue{0};        // GVC_TRACE: where the workers' time goes
     auto now_ns = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1190,66 +1205,87 @@ int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_
             uint64_t t2 = 0;
             cudaError_t e = cudaSuccess;
             if (it < n_vchunks) {
-                const uint32_t first = (uint32_t)(it * kVChunk), cnt = std::min<uint32_t>(kVChunk, n - first);
-                uint32_t *b = reinterpret_cast<uint32_t *>(host), *en = b + kVChunk, *w_ = en + kVChunk, *nw = w_ + kVChunk;
+                const uint32_t first = (uint32_t)(it * v_chunk), cnt = std::min<uint32_t>(v_chunk, n - first);
+                uint32_t *b = reinterpret_cast<uint32_t *>(host), *en = b + v_chunk, *w_ = en + v_chunk, *nw = w_ + v_chunk;
+                float *xs = reinterpret_cast<float *>(nw + v_chunk);
                 fill_vertices(user, first, cnt, b, en, w_, nw);
+                if (x) std::memcpy(xs, x + first, (size_t)cnt * sizeof(float));
                 t2 = tr.on ? now_ns() : 0;
                 e = cudaMemcpyAsync(c->d_rb.p + first, b, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_re.p + first, en, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(c->own_W.p + first, w_, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(c->own_NW.p + first, nw, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
+                if (e == cudaSuccess && x) e = cudaMemcpyAsync(c->d_x.p + first, xs, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
             } else {
-                const uint64_t off = (it - n_vchunks) * kSChunk, cnt = std::min<uint64_t>(kSChunk, span_len - off);
+                const uint64_t off = (it - n_vchunks) * s_chunk, cnt = std::min<uint64_t>(s_chunk, span_len - off);
                 fill_span(user, off, cnt, reinterpret_cast<uint32_t *>(host));
                 t2 = tr.on ? now_ns() : 0;
                 e = cudaMemcpyAsync(c->d_span.p + off, host, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->copy_stream);
             }
             if (e == cudaSuccess) e = cudaEventRecord(c->slot_ev[slot], c->copy_stream);
             if (e != cudaSuccess) { err = 1000 + (int)e; break; }
+            if (it < n_vchunks) v_issued.fetch_add(1);
             if (tr.on) { ns_wait += t1 - t0; ns_fill += t2 - t1; ns_issue += now_ns() - t2; }
         }
     };
-    if (workers == 1) {
-        work(0);
+    // ---- device side, part 1 (needs the per-vertex arrays only): degrees -> offsets, degree schedule.
+    // With helper threads this runs on the calling thread WHILE the span chunks are still being filled
+    // and copied: the vertex chunks are the first items, the event below follows their copies.
+    uint64_t nnz = 0;
+    auto offsets_and_schedule = [&]() -> int {
+        if (n) {
+            range_block_sums_kernel<<<n_scan, 256, 0, c->stream>>>(c->d_rb.p, c->d_re.p, n, span_len, c->d_blk.p, c->d_flag.p);
+            range_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(c->d_blk.p, n_scan);
+            GVC_CUDA(cudaGetLastError());
+            c->launches += 2;
+            uint32_t flag = 0;
+            GVC_CUDA(cudaMemcpyAsync(&nnz, c->d_blk.p + n_scan, sizeof(nnz), cudaMemcpyDeviceToHost, c->stream));
+            GVC_CUDA(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
+            GVC_CUDA(cudaStreamSynchronize(c->stream));
+            if (flag & kBadRange) return fail(GVC_ERR_ARG, "a vertex range is reversed or ends past the edge span");
+            if (nnz >= (1ull << 32)) return fail(GVC_ERR_UNSUPPORTED, "graph has %llu adjacency entries; 2^32 is the limit", (unsigned long long)nnz);
+            range_row_ptr_kernel<<<n_scan, 256, 0, c->stream>>>(c->d_rb.p, c->d_re.p, n, span_len, c->d_blk.p, c->own_row_ptr.p);
+            GVC_CUDA(cudaGetLastError());
+            c->launches++;
+        }
+        // the degree schedule needs offsets and weights only; the lists are moved class by class afterwards
+        int r = set_graph_views(c, n, 0, n, c->own_row_ptr.p, c->own_col.p, c->own_W.p, c->own_NW.p, nnz);
+        c->have_graph = false;                                   // not before the adjacency is in place and checked
+        return r;
+    };
+    int rc_sched = 0;
+    if (workers == 1 && n_items <= 4) {
+        work(0);                                                  // tiny graph: no helper thread
+        if (err.load()) { cudaStreamSynchronize(c->copy_stream); return fail(err.load(), "streamed upload: a copy failed"); }
+        GVC_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
+        tr.tick("stream: fill + copies issued");
+        GVC_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+        rc_sched = offsets_and_schedule();
     } else {
         std::vector<std::thread> th;
-        for (int w = 1; w < workers; ++w) th.emplace_back(work, w);
-        work(0);
+        for (int w = 0; w < workers; ++w) th.emplace_back(work, w);
+        while (v_issued.load() < n_vchunks && !err.load()) std::this_thread::yield();
+        cudaError_t e = cudaSuccess;
+        if (!err.load()) {
+            e = cudaEventRecord(c->ev_vert, c->copy_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_vert, 0);
+            if (e == cudaSuccess) rc_sched = offsets_and_schedule();
+        }
         for (auto &t : th) t.join();
+        if (e != cudaSuccess) { cudaStreamSynchronize(c->copy_stream); return fail(1000 + (int)e, "streamed upload: %s", cudaGetErrorString(e)); }
+        if (err.load()) { cudaStreamSynchronize(c->copy_stream); return fail(err.load(), "streamed upload: a copy failed"); }
+        GVC_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
+        tr.tick("stream: fill + copies, offsets + schedule meanwhile");
+        GVC_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
     }
-    if (err.load()) { cudaStreamSynchronize(c->copy_stream); return fail(err.load(), "streamed upload: a copy failed"); }
-    GVC_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
     if (tr.on)
-        std::fprintf(stderr, "gvc trace: stream: %d workers, %llu items; per worker: wait for a slot %.3f ms, fill %.3f ms, issue %.3f ms\n",
-                     workers, (unsigned long long)n_items, ns_wait.load() * 1e-6 / workers, ns_fill.load() * 1e-6 / workers,
+        std::fprintf(stderr, "gvc trace: stream: %d workers, %llu items of %zu KB; per worker: wait for a slot %.3f ms, fill %.3f ms, issue %.3f ms\n",
+                     workers, (unsigned long long)n_items, c->slot_bytes >> 10, ns_wait.load() * 1e-6 / workers, ns_fill.load() * 1e-6 / workers,
                      ns_issue.load() * 1e-6 / workers);
-    tr.tick("stream: fill + copies issued");
+    if (rc_sched) { cudaStreamSynchronize(c->copy_stream); return rc_sched; }
+    tr.tick("stream: offsets + schedule");
 
-    // ---- device side: degrees -> offsets, lists -> packed CSR, checks -----------------------------
-    GVC_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
-    uint64_t nnz = 0;
-    if (n) {
-        range_block_sums_kernel<<<n_scan, 256, 0, c->stream>>>(c->d_rb.p, c->d_re.p, n, span_len, c->d_blk.p, c->d_flag.p);
-        range_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(c->d_blk.p, n_scan);
-        GVC_CUDA(cudaGetLastError());
-        c->launches += 2;
-        uint32_t flag = 0;
-        GVC_CUDA(cudaMemcpyAsync(&nnz, c->d_blk.p + n_scan, sizeof(nnz), cudaMemcpyDeviceToHost, c->stream));
-        GVC_CUDA(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
-        GVC_CUDA(cudaStreamSynchronize(c->stream));
-        if (flag & kBadRange) return fail(GVC_ERR_ARG, "a vertex range is reversed or ends past the edge span");
-        if (nnz >= (1ull << 32)) return fail(GVC_ERR_UNSUPPORTED, "graph has %llu adjacency entries; 2^32 is the limit", (unsigned long long)nnz);
-        range_row_ptr_kernel<<<n_scan, 256, 0, c->stream>>>(c->d_rb.p, c->d_re.p, n, span_len, c->d_blk.p, c->own_row_ptr.p);
-        GVC_CUDA(cudaGetLastError());
-        c->launches++;
-    }
-    tr.tick("stream: offsets");
-    // the degree schedule needs offsets and weights only; the lists are then moved class by class
-    if ((rc = set_graph_views(c, n, 0, n, c->own_row_ptr.p, c->own_col.p, c->own_W.p, c->own_NW.p, nnz))) {
-        c->have_graph = false;
-        return rc;
-    }
-    tr.tick("stream: schedule");
+    // ---- device side, part 2: lists -> packed CSR, id checks -------------------------------------
     if (nnz) {
         const Schedule &sc = c->sched;
         const uint64_t warp_tasks = (uint64_t)sc.n_chunks16 * 8 + sc.n_mid + (n - sc.n_ring - sc.n_mid + 31) / 32;
@@ -1259,6 +1295,7 @@ int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_
         GVC_CUDA(cudaGetLastError());
         c->launches++;
     }
+    c->have_graph = true;
     if ((rc = build_peer_mask(c))) { c->have_graph = false; return rc; }
     uint32_t flag = 0;
     GVC_CUDA(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, c->stream));
@@ -1268,7 +1305,13 @@ int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_
         c->have_graph = false;
         return fail(GVC_ERR_ARG, "a neighbour id is >= %u vertices", n);
     }
+    if (x) c->x_resident_n = n;
     return 0;
+}
+
+int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_vertices_fn fill_vertices,
+                            gvc_fill_span_fn fill_span, void *user, int n_threads) {
+    return gvc_graph_upload_stream_x(c, n, span_len, fill_vertices, fill_span, user, n_threads, nullptr);
 }
 
 int gvc_graph_staging(gvc_ctx *c, uint32_t n_local, uint64_t nnz, uint64_t **row_ptr, uint32_t **col,
@@ -1466,15 +1509,16 @@ int gvc_forward(gvc_ctx *c, const float *x, float scale, float *scores, int mode
     if (!c->have_graph) return fail(GVC_ERR_STATE, "no graph uploaded");
     const uint32_t n = c->n_global;
     if (n == 0) return 0;
-    if (!x || !scores) return fail(GVC_ERR_ARG, "null buffer");
+    if (!scores) return fail(GVC_ERR_ARG, "null buffer");
+    if (!x && c->x_resident_n != n) return fail(GVC_ERR_ARG, "x is null and no input came with the graph (gvc_graph_upload_stream_x)");
     if ((rc = use_device(c))) return rc;
     Tracer tr;
     // x goes up and the scores come back through the ring of pinned slots (the same one the streamed
-    // graph upload uses): nothing of the graph's size is pinned per call
+    // graph upload uses): nothing of the graph's size is pinned per call.  x = NULL: it came with the graph.
     if ((rc = ensure_ring(c, 16, 256u << 10))) return rc;
     const size_t per = c->slot_bytes / sizeof(float);
     const size_t chunks = ((size_t)n + per - 1) / per;
-    for (size_t k = 0; k < chunks; ++k) {
+    for (size_t k = 0; x && k < chunks; ++k) {
         const int slot = (int)(k % c->n_slots);
         const size_t off = k * per, cnt = std::min(per, (size_t)n - off);
         float *host = reinterpret_cast<float *>(c->ring.p + (size_t)slot * c->slot_bytes);
@@ -1483,6 +1527,7 @@ int gvc_forward(gvc_ctx *c, const float *x, float scale, float *scores, int mode
         GVC_CUDA(cudaMemcpyAsync(c->d_x.p + off, host, cnt * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         GVC_CUDA(cudaEventRecord(c->slot_ev[slot], c->stream));
     }
+    if (x) c->x_resident_n = 0;
     tr.tick("forward: x up");
     // the selection keys are a by-product of stage 2 (5 bytes per vertex): kept on the device for gvc_last_keys
     const bool own_keys = c->fused && !c->keys_out;

@@ -190,7 +190,8 @@ void read_span(void *user, uint64_t offset, uint64_t count, uint32_t *dst) {
 }
 
 // Upload g into the context; returns the number of entries that travelled (for the profile line).
-uint64_t upload_graph_streamed(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g) {
+// x (may be null): predict's input, which then travels with the per-vertex arrays (gvc_graph_upload_stream_x).
+uint64_t upload_graph_streamed(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g, const float *x) {
     const Tn n = g.size();
     graph_reader r{&g, n ? g.begin(0) : std::vector<Tn>::const_iterator(), 0, nullptr};
     // where does the live part of the edge vector start and stop, and how much of it is live?
@@ -243,7 +244,7 @@ uint64_t upload_graph_streamed(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g) {
         r.prefix = prefix.data();
         span_len = nnz;
     }
-    const int rc = gvc_graph_upload_stream(ctx, n, span_len, read_vertices, read_span, &r, 0);
+    const int rc = gvc_graph_upload_stream_x(ctx, n, span_len, read_vertices, read_span, &r, 0, x);
     if (rc != 0) gvc_host::die("gvc_graph_upload_stream", rc);
     return span_len;
 }
@@ -255,11 +256,12 @@ bool use_packed_upload() {
     return packed;
 }
 
-void upload_graph(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g, uint64_t *entries, double *t_extract) {
+// Returns true when x went up with the graph (the forward is then called without it).
+bool upload_graph(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g, uint64_t *entries, double *t_extract, const float *x = nullptr) {
     if (!use_packed_upload()) {
         *t_extract = 0;
-        *entries = upload_graph_streamed(ctx, g);
-        return;
+        *entries = upload_graph_streamed(ctx, g, x);
+        return x != nullptr;
     }
     const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     const csr_view s = extract_csr(ctx, g);
@@ -267,6 +269,7 @@ void upload_graph(gvc_ctx *ctx, const reduction_graph<Tn, Tw> &g, uint64_t *entr
     const int rc = gvc_graph_upload(ctx, g.size(), s.row_ptr, s.col, s.w, s.nw);
     if (rc != 0) gvc_host::die("gvc_graph_upload", rc);
     *entries = s.nnz;
+    return false;
 }
 
 // GVC_PROFILE=1: per-call and cumulative timing of predict() on stderr (CSR extraction on the
@@ -459,9 +462,9 @@ void model::predict(const matrix &in, matrix &out, const reduction_graph<Tn, Tw>
     const double t0 = now_s();
     uint64_t entries = 0;
     double t_extract = 0;
-    upload_graph(ctx, g, &entries, &t_extract);
+    const bool x_sent = upload_graph(ctx, g, &entries, &t_extract, in.get_width() == 1 && in.get_height() == n ? cdata(in) : nullptr);
     const double t2 = now_s();
-    const int rc = gvc_forward(ctx, cdata(in), scale, mdata(out), gvc_host::mode());
+    const int rc = gvc_forward(ctx, x_sent ? nullptr : cdata(in), scale, mdata(out), gvc_host::mode());
     if (rc != 0) gvc_host::die("gvc_forward", rc);
     const double t3 = now_s();
     pf.calls++; pf.extract += t_extract; pf.upload += t2 - t0 - t_extract; pf.forward += t3 - t2;

@@ -134,6 +134,13 @@ typedef void (*gvc_fill_vertices_fn)(void *user, uint32_t first, uint32_t count,
 typedef void (*gvc_fill_span_fn)(void *user, uint64_t offset, uint64_t count, uint32_t *dst);
 int gvc_graph_upload_stream(gvc_ctx *ctx, uint32_t n, uint64_t span_len, gvc_fill_vertices_fn fill_vertices,
                             gvc_fill_span_fn fill_span, void *user, int n_threads);
+/* The same, and the forward's input travels along: x[0..n) (the `in` of model::predict,
+ * src/GNN_VC.cpp:189-191) is copied by the worker threads next to W and NW, so the single-threaded
+ * staging copy of gvc_forward drops out of predict's critical path.  A following
+ * gvc_forward(ctx, NULL, ...) uses it (any number of times, until the next graph upload or a forward
+ * with an explicit x).  x == NULL: exactly gvc_graph_upload_stream. */
+int gvc_graph_upload_stream_x(gvc_ctx *ctx, uint32_t n, uint64_t span_len, gvc_fill_vertices_fn fill_vertices,
+                              gvc_fill_span_fn fill_span, void *user, int n_threads, const float *x);
 
 /* Same shard description with DEVICE pointers that stay owned by the caller and
  * must outlive the context's use of them (no copy; row_ptr is uint32 here, the
@@ -158,6 +165,7 @@ int gvc_graph_set_tail(gvc_ctx *ctx, int has_tail, uint32_t local_index);
  * set_weight_scale src/gnn_inference.cpp:83-90), scores[n] (= out(u,0)).  Includes
  * the host->device copy of x and the device->host copy of the scores.  n == 0
  * is a no-op (the reference is called with an empty graph).
+ * x == NULL: use the input that came with the graph (gvc_graph_upload_stream_x); an error if none did.
  * Single-shard contexts only. */
 int gvc_forward(gvc_ctx *ctx, const float *x, float weight_scale, float *scores, int mode);
 

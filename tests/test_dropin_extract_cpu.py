@@ -68,9 +68,14 @@ def test_predict_hands_over_exactly_the_graph_the_reference_sees(mock, reference
     for rounds in range(5):
         n = reference.graph_size(gr)
         assert ours.graph_size(go) == n
-        x = np.ones(n, np.float32)
+        x = (np.arange(n, dtype=np.float32) * np.float32(0.25) + np.float32(rounds)).astype(np.float32)
         out = ours.predict_on(ho, go, x, 200.0)
         assert out.shape == (n,) and (n == 0 or np.all(out == 0.5))         # the mock's "scores" made it into `out`
+        if n:                                                                # predict's input travelled with the graph
+            ours.L.mock_last_x.restype = C.c_uint64
+            ours.L.mock_last_x.argtypes = [po._f32p]
+            got = np.empty(n, np.float32)
+            assert ours.L.mock_last_x(po._p(got, po._f32p)) == n and np.array_equal(got, x)
         rp, col, w, nw, act = reference.graph_csr(gr)
         rp2, col2, w2, nw2, span, streamed = last_graph(ours, n)
         assert streamed

@@ -533,6 +533,25 @@ def test_streamed_upload_builds_the_same_graph(ctx, oracle, oracle_model):
     for threads in (1, 3, 0):
         ctx.graph_upload_ranges(span, b, e, W, NW, n_threads=threads)
         assert_bit_equal(ctx.forward(x, s), want, f"rmat16 streamed, {threads} threads")
+    # the forward's input travelling with the graph (gvc_graph_upload_stream_x), forward(x = NULL) -- twice
+    ctx.graph_upload_ranges(span, b, e, W, NW, n_threads=3, x=x)
+    assert_bit_equal(ctx.forward(None, s), want, "rmat16 streamed with x")
+    assert_bit_equal(ctx.forward(None, s), want, "rmat16 streamed with x, second forward")
+    x2 = (x * np.float32(0.5)).astype(np.float32)
+    want2 = ctx.forward(x2, s)                                    # an explicit x replaces it ...
+    with pytest.raises(capi.GvcError, match="x is null"):         # ... and the resident one is gone
+        ctx.forward(None, s)
+    ctx.graph_upload_ranges(span, b, e, W, NW, x=x2)
+    assert_bit_equal(ctx.forward(None, s), want2, "rmat16 streamed with another x")
+    ctx.graph_upload_ranges(span, b, e, W, NW)                    # no x came with this graph
+    with pytest.raises(capi.GvcError, match="x is null"):
+        ctx.forward(None, s)
+    g2 = graphs.rmat_graph(20, 8, seed=10)                        # > 32 MB: the 1 MB slots, overlapped schedule
+    rp, col, W, NW, x, s = inputs_of(g2)
+    ctx.graph_upload(rp, col, W, NW)
+    want = ctx.forward(x, s)
+    ctx.graph_upload_ranges(col, rp[:-1].astype(np.uint32), rp[1:].astype(np.uint32), W, NW, x=x)
+    assert_bit_equal(ctx.forward(None, s), want, "rmat20 streamed with x, large slots")
     ctx.graph_upload_ranges(np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.uint32),
                             np.zeros(0, np.uint32), np.zeros(0, np.uint32))          # predict on an empty graph
     assert ctx.forward(np.zeros(0, np.float32), 200.0).size == 0

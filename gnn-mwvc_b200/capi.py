@@ -37,6 +37,7 @@ SIGNATURES = {
     "gvc_graph_upload_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u32p, _u32p, _u32p]),
     "gvc_graph_staging": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(_u64p), C.POINTER(_u32p),
                                     C.POINTER(_u32p), C.POINTER(_u32p)]),
+    "gvc_ctx_warm": (C.c_int, [C.c_void_p, C.c_uint64]),
     "gvc_graph_upload_stream": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "gvc_graph_upload_stream_x": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gvc_graph_adopt_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1309,6 +1309,22 @@ int gvc_graph_upload_stream_x(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fil
     return 0;
 }
 
+int gvc_ctx_warm(gvc_ctx *c, uint64_t graph_bytes_hint) {
+    int rc;
+    if ((rc = check_ctx(c))) return rc;
+    if ((rc = use_device(c))) return rc;
+    // what the first streamed upload would otherwise pay for inside predict(): pinning the ring (about
+    // 0.5 ms per MB) and the first device allocation
+    const bool large = graph_bytes_hint == 0 || graph_bytes_hint >= (32ull << 20);
+    if ((rc = ensure_ring(c, 16, large ? ((size_t)1 << 20) : ((size_t)256 << 10)))) return rc;
+    if (graph_bytes_hint) {
+        c->arena.next_chunk = (size_t)std::min<uint64_t>(graph_bytes_hint, 8ull << 30);
+        void *p = c->arena.alloc(256);
+        if (!p) return GVC_ERR_ALLOC;
+    }
+    return 0;
+}
+
 int gvc_graph_upload_stream(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fill_vertices_fn fill_vertices,
                             gvc_fill_span_fn fill_span, void *user, int n_threads) {
     return gvc_graph_upload_stream_x(c, n, span_len, fill_vertices, fill_span, user, n_threads, nullptr);

@@ -495,6 +495,7 @@ std::ostream &gnn::operator<<(std::ostream &os, const model &m) {
 }
 
 std::istream &gnn::operator>>(std::istream &is, model &m) {
+    gvc_host::warm_start();                         // the GPU gets ready while the caller goes on to parse its graph
     size_t count = 0;
     std::string word;
     is >> m.name >> count >> word;                  // "<name> <n> Layers"

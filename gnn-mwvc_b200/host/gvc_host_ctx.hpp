@@ -4,6 +4,7 @@
 // created lazily at first use.  Environment:
 //   GVC_DEVICE  CUDA ordinal (default 0)
 //   GVC_MODE    "exact" (default, bit-identical scores) or "fast"
+//   GVC_WARM    0: no early context creation on a helper thread (see warm_start)
 //   GVC_DEVICES "0,1,2,3": predict() shards graphs of at least GVC_MULTI_MIN_VERTICES vertices
 //               (default 2 000 000) over these devices (gvc_group, include/gvc.h); smaller graphs and
 //               everything else stay on the first of them
@@ -14,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "gvc.h"
@@ -42,16 +45,44 @@ inline const std::vector<int> &devices() {
     return list;
 }
 
-inline gvc_ctx *context() {
-    static gvc_ctx *ctx = [] {
+// The context is created at first use -- or ahead of time by warm_start(): CUDA initialisation (a few
+// hundred ms in a fresh process) and the pinning of the upload ring (about 8 ms) then happen on a helper
+// thread while the solver still parses and reduces its graph, instead of inside the first predict().
+inline gvc_ctx *context_impl(bool fatal, bool warm) {
+    static std::mutex mu;
+    static gvc_ctx *ctx = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ctx) {
         const char *dev = std::getenv("GVC_DEVICE");
         gvc_ctx *c = nullptr;
         const int ordinal = dev ? std::atoi(dev) : (devices().empty() ? 0 : devices()[0]);
         const int rc = gvc_ctx_create(&c, ordinal);
-        if (rc != 0) die("gvc_ctx_create", rc);
-        return c;
-    }();
+        if (rc != 0) {
+            if (fatal) die("gvc_ctx_create", rc);
+            return nullptr;                    // the helper thread leaves the complaint to the call that needs the GPU
+        }
+        if (warm) gvc_ctx_warm(c, 0);          // best effort
+        ctx = c;
+    }
     return ctx;
+}
+
+inline gvc_ctx *context() { return context_impl(true, false); }
+
+// Called where the solver builds its model (operator>>, src/GNN_VC.cpp:263 -- before it parses the graph).
+// GVC_WARM=0 turns it off.  The thread is joined at exit.
+inline void warm_start() {
+    struct helper {
+        std::thread t;
+        ~helper() { if (t.joinable()) t.join(); }
+    };
+    static std::once_flag once;
+    static helper h;
+    std::call_once(once, [] {
+        const char *e = std::getenv("GVC_WARM");
+        if (e && e[0] == '0') return;
+        h.t = std::thread([] { context_impl(false, true); });
+    });
 }
 
 // the group of GVC_DEVICES (null when fewer than two are named)

@@ -158,6 +158,11 @@ int gvc_graph_adopt_device(gvc_ctx *ctx, uint32_t n_global, uint32_t v_begin, ui
  * upload/adopt (which resets to the default). */
 int gvc_graph_set_tail(gvc_ctx *ctx, int has_tail, uint32_t local_index);
 
+/* Optional: pay the one-off costs of the first streamed upload NOW (pinning the ring of upload slots,
+ * the first device allocation of about graph_bytes_hint bytes; 0 = ring only) instead of inside the first
+ * predict.  The drop-in calls it from a helper thread while the solver still parses and reduces the graph. */
+int gvc_ctx_warm(gvc_ctx *ctx, uint64_t graph_bytes_hint);
+
 /* ---- forward: gnn::model::predict (src/gnn_inference.cpp:67-81) ------------ */
 
 /* Whole forward with HOST buffers: x[n] (= in(u,0), src/GNN_VC.cpp:189-191),

@@ -30,6 +30,7 @@ struct gvc_ctx { int dummy; };
 extern "C" {
 const char *gvc_last_error(void) { return "mock"; }
 int gvc_ctx_create(gvc_ctx **out, int) { static gvc_ctx c; *out = &c; return 0; }
+int gvc_ctx_warm(gvc_ctx *, uint64_t) { return 0; }
 int gvc_model_upload(gvc_ctx *, int, const int *, const int *, const int *, const float *const *, const float *const *) { return 0; }
 int gvc_model_weight_scales(gvc_ctx *, int n, const float *s) { g_n_scales = n; for (int i = 0; i < n && i < 8; ++i) g_scales[i] = s[i]; return 0; }
 

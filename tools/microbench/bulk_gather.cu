@@ -1,5 +1,9 @@
-// bulk_gather.cu -- PREPARED FOR THE NEXT ROUND, compile-checked only (written after round 1's GPU
-// budget was spent; no number from it appears anywhere yet).
+// bulk_gather.cu -- can the 64-byte neighbour rows be gathered with the bulk-copy engine?
+// MEASURED in round 2 (profiles/r2_microbench_bulk_gather_rmat_ids.txt, the id stream of the R-MAT
+// benchmark graph): NO.  3.0 TB/s of row bytes with 2-4 batches in flight per warp, 1.6 TB/s with 8
+// (LDG.128 gathers of the same ids: 9-13 TB/s, gather_bw.cu), and 4.7 ns per neighbour for a single
+// hub on one CTA (the exact chain runs at 2.9-3.4).  One 64-byte copy per bulk instruction is far below
+// the granularity the engine is built for; the row gathers stay on LDG.128.
 //
 // Question: can the 64-byte neighbour rows be gathered with the bulk-copy engine
 // (cp.async.bulk.shared::cluster.global + mbarrier complete_tx, "TMA 1-D") instead of LDG.128 per

@@ -38,6 +38,24 @@ SIGNATURES = {
     "gvc_graph_staging": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(_u64p), C.POINTER(_u32p),
                                     C.POINTER(_u32p), C.POINTER(_u32p)]),
     "gvc_ctx_warm": (C.c_int, [C.c_void_p, C.c_uint64]),
+    # training path
+    "gvc_trainer_create": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p, _i32p, C.POINTER(_f32p), C.POINTER(_f32p), C.POINTER(C.c_void_p)]),
+    "gvc_trainer_destroy": (None, [C.c_void_p]),
+    "gvc_trainer_input_width": (C.c_int, [C.c_void_p]),
+    "gvc_trainer_output_width": (C.c_int, [C.c_void_p]),
+    "gvc_trainer_predict": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, _f32p, C.c_int]),
+    "gvc_trainer_backprop": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int]),
+    "gvc_trainer_mse_backprop": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int]),
+    "gvc_trainer_sgd_step": (C.c_int, [C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_float]),
+    "gvc_trainer_zero_grad": (C.c_int, [C.c_void_p]),
+    "gvc_trainer_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, _f32p]),
+    "gvc_trainer_write": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, _f32p]),
+    "gvc_linear_backward_host": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int]),
+    "gvc_graph_backward_host": (C.c_int, [C.c_void_p, _f32p, C.c_int, _f32p]),
+    "gvc_relu_backward_host": (C.c_int, [C.c_void_p, C.c_uint64, _f32p, _f32p, _f32p]),
+    "gvc_sigmoid_backward_host": (C.c_int, [C.c_void_p, C.c_uint64, _f32p, _f32p, _f32p, C.c_int]),
+    "gvc_mse_host": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, _f32p, _f32p, _f32p, _f32p]),
+    "gvc_sgd_host": (C.c_int, [C.c_void_p, C.c_uint64, _f32p, _f32p, _f32p, C.c_uint64, C.c_float, C.c_float, C.c_float]),
     "gvc_graph_upload_stream": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "gvc_graph_upload_stream_x": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gvc_graph_adopt_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -475,6 +493,76 @@ class Group:
         out = np.empty(self.n, np.float32)
         self._check(self.lib.gvc_group_forward(self.h, _ptr(x, _f32p), float(weight_scale), _ptr(out, _f32p), mode))
         return out
+
+
+class Trainer:
+    """gvc_trainer: a model_training on the device (reference old_files/src/lib/gnn_training.cpp).  The graph is
+    the context's current graph."""
+
+    def __init__(self, ctx: "Context", layers):
+        self.ctx, self.lib, self.layers = ctx, ctx.lib, layers
+        n = len(layers)
+        kinds = (C.c_int * n)(*[int(k) for k, _, _ in layers])
+        rows, cols = (C.c_int * n)(), (C.c_int * n)()
+        Wp, bp = (_f32p * n)(), (_f32p * n)()
+        keep = []
+        for i, (k, W, b) in enumerate(layers):
+            if k == LINEAR:
+                W = _np(W, np.float32)
+                b = _np(b, np.float32).ravel()
+                rows[i], cols[i] = W.shape
+                Wp[i], bp[i] = W.ctypes.data_as(_f32p), b.ctypes.data_as(_f32p)
+                keep += [W, b]
+        h = C.c_void_p()
+        ctx._check(self.lib.gvc_trainer_create(ctx.h, n, kinds, rows, cols, Wp, bp, C.byref(h)))
+        self.h = h
+        self.in_w, self.out_w = self.lib.gvc_trainer_input_width(h), self.lib.gvc_trainer_output_width(h)
+
+    def close(self):
+        if self.h:
+            self.lib.gvc_trainer_destroy(self.h)
+            self.h = None
+
+    def predict(self, x, scales, mode: int = MODE_EXACT, want_out: bool = True):
+        n = self.ctx.n_global
+        x = _np(x, np.float32).reshape(n, -1)
+        if x.shape[1] != self.in_w:
+            raise GvcError(f"x is {x.shape[1]} wide, the model takes {self.in_w}")
+        sc = _np(np.atleast_1d(scales), np.float32)
+        out = np.empty((n, self.out_w), np.float32) if want_out else None
+        self.ctx._check(self.lib.gvc_trainer_predict(self.h, _ptr(x, _f32p), _ptr(sc, _f32p), sc.size,
+                                                     _ptr(out, _f32p) if want_out else None, mode))
+        return out
+
+    def backprop(self, grad, mode: int = MODE_EXACT, want_grad_x: bool = True):
+        n = self.ctx.n_global
+        grad = _np(grad, np.float32).reshape(n, -1)
+        gx = np.empty((n, self.in_w), np.float32) if want_grad_x else None
+        self.ctx._check(self.lib.gvc_trainer_backprop(self.h, _ptr(grad, _f32p), _ptr(gx, _f32p) if want_grad_x else None, mode))
+        return gx
+
+    def mse_backprop(self, y, mode: int = MODE_EXACT) -> float:
+        y = _np(y, np.float32).reshape(self.ctx.n_global, -1)
+        loss = C.c_float()
+        self.ctx._check(self.lib.gvc_trainer_mse_backprop(self.h, _ptr(y, _f32p), C.cast(C.byref(loss), _f32p), mode))
+        return float(loss.value)
+
+    def sgd_step(self, batch_size: int, lr=0.1, momentum=0.9, weight_decay=0.0):
+        self.ctx._check(self.lib.gvc_trainer_sgd_step(self.h, batch_size, lr, momentum, weight_decay))
+
+    def zero_grad(self):
+        self.ctx._check(self.lib.gvc_trainer_zero_grad(self.h))
+
+    def read(self, what: int, layer: int):
+        """(W-shaped, bias-shaped) arrays: what = 0 parameters, 1 gradients, 2 velocities."""
+        W = np.empty(np.asarray(self.layers[layer][1]).shape, np.float32)
+        b = np.empty(W.shape[1], np.float32)
+        self.ctx._check(self.lib.gvc_trainer_read(self.h, what, layer, _ptr(W, _f32p), _ptr(b, _f32p)))
+        return W, b
+
+    def write(self, what: int, layer: int, W, b):
+        W, b = _np(W, np.float32), _np(b, np.float32).ravel()
+        self.ctx._check(self.lib.gvc_trainer_write(self.h, what, layer, _ptr(W, _f32p), _ptr(b, _f32p)))
 
 
 def parse_metis(path, n_threads: int = 0, csr: bool = False):

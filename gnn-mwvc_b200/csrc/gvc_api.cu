@@ -2012,3 +2012,5 @@ const float *gvc_debug_h(const gvc_ctx *c, int which) {
 }
 
 }  // extern "C"
+
+#include "gvc_train_api.cuh"

@@ -381,9 +381,22 @@ __device__ __noinline__ float px_slow16(float *__restrict__ T, const float4 *__r
     __syncwarp();
     return acc;
 }
+// the 64 rows of batch b (4 KB = 32 lines, one per lane) on their way into L1: no register, no scoreboard
+__device__ __forceinline__ void px_prefetch_batch16(const float4 *__restrict__ rows, uint32_t b, int lane) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(rows + (size_t)64 * b * 4 + 8 * lane));
+}
 
 // ---- phase C: one warp walks the batches of hub g in order; returns the sums (lane c, c < W; mirrored) ---
-// T: the warp's tile buffer in shared memory (slow batches are staged there, column-major, like the ring's)
+// T: the warp's tile buffer in shared memory (slow batches are staged there, column-major, like the ring's).
+// The walk is one dependent chain, so what counts is the latency per batch.  Measured on a 262 144-neighbour
+// star (tools/chain_probe.py) a batch-by-batch loop cost 184 cycles per clean batch (shared-memory load,
+// shuffle, vote and branch all behind the running sum) and ~1000 per dirty one (its rows were only
+// requested when it was reached).  Hence:
+//   * four batches are checked at once: their P / D come out of shared memory before the sum is needed,
+//     the four dependent FADDs follow each other directly, ONE vote decides whether all four were clean
+//     (else the quad is redone batch by batch, which is always right);
+//   * the rows of the next batch flagged dirty by phase B are prefetched into L1 as soon as it is known to
+//     be next, i.e. while the clean batches before it are walked.
 __device__ __noinline__ float px_walk16(const PxArgs &px, uint32_t g, uint32_t deg, float *__restrict__ T, int lane) {
     const uint2 hi = __ldg(px.info + g);
     const long long t_in = clock64();
@@ -401,21 +414,54 @@ __device__ __noinline__ float px_walk16(const PxArgs &px, uint32_t g, uint32_t d
     const uint32_t nq = (nb + 3) / 4;                                // quads of batches (the arrays are padded to whole chunks)
     float acc = 0.0f;
     uint32_t slow = 0;
+    // The records were written by other SMs (st.cg): a load of them is an L2 access, 500-600 cycles under load,
+    // and with only the next quad in flight that latency was the walk's pace (138 cycles per batch measured).
+    // So the record stream is prefetched into L1 sixteen to twenty-four quads ahead -- one 128-byte line per
+    // lane covers eight quads -- and the register copy of the next quad then comes out of L1.
+    const float *rec_lines = px.rec + (size_t)hi.x * 64 * 32 + 32 * lane;      // lane's line of an 8-quad group (8 x 128 floats)
+    auto prefetch_quads = [&](uint32_t q0) {                                   // quads [q0, q0 + 8)
+        if (q0 < nq) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec_lines + (size_t)q0 * 128));
+    };
+    prefetch_quads(0); prefetch_quads(8); prefetch_quads(16);
     float4 rnext = rec4[0];
-    uint32_t fl = 0, fl_next = F[min((uint32_t)lane, nb - 1)];       // lane l: flag of batch (32-block base) + l
+    // dirty: bit i = batch (32-block base) + i was flagged by phase B; the next block's flags are in flight
+    uint32_t dirty = 0, fl_next = F[min((uint32_t)lane, nb - 1)];
+    uint32_t pre_b = 0xFFFFFFFFu;                                    // the batch whose rows were requested ahead (L1 prefetch)
 #pragma unroll 1
     for (uint32_t qd = 0; qd < nq; ++qd) {
-        if ((qd & 7u) == 0) { fl = fl_next; fl_next = F[min(4 * qd + 32 + lane, nb - 1)]; }
+        if ((qd & 7u) == 0) {
+            dirty = __ballot_sync(0xffffffffu, fl_next != 0u);
+            fl_next = F[min(4 * qd + 32 + lane, nb - 1)];
+            prefetch_quads(qd + 24);
+        }
         __syncwarp();
         reinterpret_cast<float4 *>(R)[lane] = rnext;
         rnext = rec4[(size_t)min(qd + 1, nq - 1) * 32];
+        // the next dirty batch of this 32-block at or after this quad: get its rows under way
+        const uint32_t ahead = dirty >> ((4 * qd) & 31u);
+        if (ahead != 0u && pre_b == 0xFFFFFFFFu) {
+            const uint32_t nd = 4 * qd + (uint32_t)__ffs((int)ahead) - 1;
+            if (nd < nb) { pre_b = nd; px_prefetch_batch16(rows, nd, lane); }
+        }
         __syncwarp();
+        if ((ahead & 0xFu) == 0u && 4 * qd + 4 <= nb) {
+            // all four at once
+            const float P0 = R[c], D0 = R[16 + c], P1 = R[32 + c], D1 = R[48 + c];
+            const float P2 = R[64 + c], D2 = R[80 + c], P3 = R[96 + c], D3 = R[112 + c];
+            const uint32_t m0 = px_entry_binade(P0), m1 = px_entry_binade(P1), m2 = px_entry_binade(P2), m3 = px_entry_binade(P3);
+            const float a1 = __fadd_rn(acc, D0), a2 = __fadd_rn(a1, D1), a3 = __fadd_rn(a2, D2), a4 = __fadd_rn(a3, D3);
+            const bool ok = ((P0 < 0.0f) | (((__float_as_uint(acc) & 0x7F800000u) == m0) & (a1 < __uint_as_float(m0 + (1u << 23))))) &
+                            ((P1 < 0.0f) | (((__float_as_uint(a1) & 0x7F800000u) == m1) & (a2 < __uint_as_float(m1 + (1u << 23))))) &
+                            ((P2 < 0.0f) | (((__float_as_uint(a2) & 0x7F800000u) == m2) & (a3 < __uint_as_float(m2 + (1u << 23))))) &
+                            ((P3 < 0.0f) | (((__float_as_uint(a3) & 0x7F800000u) == m3) & (a4 < __uint_as_float(m3 + (1u << 23)))));
+            if (__all_sync(0xffffffffu, ok)) { acc = a4; continue; }
+        }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             const uint32_t b = 4 * qd + j;
             if (b >= nb) break;
             const float Pj = R[32 * j + c], Dj = R[32 * j + 16 + c];
-            const uint32_t Fj = __shfl_sync(0xffffffffu, fl, b & 31u);
+            const uint32_t Fj = (dirty >> (b & 31u)) & 1u;
             const uint32_t mb = px_entry_binade(Pj);
             const float nxt = __fadd_rn(acc, Dj);
             const bool ok = (Fj == 0u) & ((Pj < 0.0f) |              // an all-zero column: D = 0, nothing to verify
@@ -425,6 +471,7 @@ __device__ __noinline__ float px_walk16(const PxArgs &px, uint32_t g, uint32_t d
             } else {                                                 // the reference's way: element by element
                 ++slow;
                 acc = px_slow16(T, rows, b, acc, lane);
+                if (pre_b <= b) pre_b = 0xFFFFFFFFu;
             }
         }
     }

@@ -352,6 +352,11 @@ void upload_model_if_stale(gvc_ctx *ctx, gvc_group *grp, const void *owner, cons
 
 }  // namespace
 
+// what the training drop-in (host/gvc_gnn_training.cpp) uploads its graphs with
+namespace gvc_host {
+void upload_graph_of(gvc_ctx *ctx, const reduction_graph<gnn::Tn, gnn::Tw> &g) { upload_graph_streamed(ctx, g, nullptr); }
+}  // namespace gvc_host
+
 // ---- linear_layer (include/gnn_inference.hpp:11-17) ----------------------------------
 // Random init as the reference's ctor, src/gnn_inference.cpp:7-18: uniform in
 // +-1/sqrt(dim_in + 1) from mt19937(seed), weights first, then bias.

@@ -319,6 +319,66 @@ int gvc_debug_px(gvc_ctx *ctx, uint32_t *out8);
 /* Device buffers of the last forward (h1/h2: n_global x 16), for tests. */
 const float *gvc_debug_h(const gvc_ctx *ctx, int which);
 
+/* ---- training path ---------------------------------------------------------
+ * Reference: old_files/src/lib/gnn_training.cpp (+ old_files/include/gnn/gnn_training.hpp): the
+ * backward pass of the four layer kinds (:17-65), model_training::predict / backprop (:81-129),
+ * MSE_loss / MSE_grad (:175-190), SGD_step (:192-224), zero_grad (:226-235).
+ *
+ * gvc_trainer is a model_training on the device: parameters, gradients and velocities of every linear
+ * layer and, between a predict and its backprop, every layer's input (the reference's in_copy).  The
+ * graph is the context's current graph (any upload path; whole-graph contexts).  GVC_MODE_EXACT: the
+ * reference's fp32 operation order everywhere, the three dot() calls of a linear layer in the order of
+ * the OpenBLAS kernel the parity tests pin (bit-identical gradients; the sum over the rows is then a
+ * sequential chain per weight -- a verification mode).  GVC_MODE_FAST: gradients reduced over the rows
+ * in parallel (deterministic; within 1e-5 of exact). */
+typedef struct gvc_trainer gvc_trainer;
+
+/* Same layer description as gvc_model_upload; gradients and velocities start at zero
+ * (linear_layer_training ctor, :7-9).  Linear layers of up to 35 x 32. */
+int gvc_trainer_create(gvc_ctx *ctx, int n_layers, const int *kinds, const int *rows, const int *cols,
+                       const float *const *W, const float *const *bias, gvc_trainer **out);
+void gvc_trainer_destroy(gvc_trainer *t);
+int gvc_trainer_input_width(const gvc_trainer *t);
+int gvc_trainer_output_width(const gvc_trainer *t);
+
+/* model_training::predict (:81-96).  x: n x input width (host); scales: WEIGHT_SCALE of every graph layer
+ * (n_scales == 1: one for all); out: n x output width (host; may be NULL -- the output stays on the
+ * device for gvc_trainer_mse_backprop). */
+int gvc_trainer_predict(gvc_trainer *t, const float *x, const float *scales, int n_scales, float *out, int mode);
+
+/* model_training::backprop (:98-129) of the last predict.  grad_in: n x output width; grad_out (may be
+ * NULL): n x input width.  Accumulates into the gradients. */
+int gvc_trainer_backprop(gvc_trainer *t, const float *grad_in, float *grad_out, int mode);
+
+/* MSE_loss + MSE_grad + backprop without leaving the device: y goes up, the loss comes back
+ * (run_model, old_files/src/apps/gnn_train.cpp:85-99). */
+int gvc_trainer_mse_backprop(gvc_trainer *t, const float *y, float *loss, int mode);
+
+int gvc_trainer_sgd_step(gvc_trainer *t, uint64_t batch_size, float lr, float momentum, float weight_decay);
+int gvc_trainer_zero_grad(gvc_trainer *t);
+
+/* what: 0 parameters, 1 gradients, 2 velocities of the linear layer at index `layer` (counted over ALL
+ * layers); W: rows x cols, bias: cols; either may be NULL. */
+int gvc_trainer_read(gvc_trainer *t, int what, int layer, float *W, float *bias);
+int gvc_trainer_write(gvc_trainer *t, int what, int layer, const float *W, const float *bias);
+
+/* Single layers with host buffers -- what the drop-in's *_training structs call, like gvc_linear_host
+ * and gvc_graph_layer_host for the forward.
+ *   linear   :17-26  in n x K (the layer's in_copy), grad_in n x Nout, W K x Nout; grad_W / grad_bias
+ *                    are accumulated into; grad_out n x K
+ *   graph    :32-42  on the context's graph: grad_in n x (2 width + 3), grad_out n x width
+ *   ReLU     :50-53  z >= 0 ? g : 0;   sigmoid :61-65  f(z) (1 - f(z)) g   (z = the layer's input)
+ *   MSE      :175-190  loss and / or grad (either may be NULL) of n x w matrices
+ *   SGD      :192-224  one parameter array with its gradient and velocity, updated in place */
+int gvc_linear_backward_host(gvc_ctx *ctx, uint64_t n, int K, int Nout, const float *in, const float *grad_in,
+                             const float *W, float *grad_W, float *grad_bias, float *grad_out, int mode);
+int gvc_graph_backward_host(gvc_ctx *ctx, const float *grad_in, int width, float *grad_out);
+int gvc_relu_backward_host(gvc_ctx *ctx, uint64_t count, const float *z, const float *grad_in, float *grad_out);
+int gvc_sigmoid_backward_host(gvc_ctx *ctx, uint64_t count, const float *z, const float *grad_in, float *grad_out, int mode);
+int gvc_mse_host(gvc_ctx *ctx, uint64_t n, int w, const float *x, const float *y, float *loss, float *grad);
+int gvc_sgd_host(gvc_ctx *ctx, uint64_t count, float *param, float *grad, float *vel, uint64_t batch_size, float lr,
+                 float momentum, float weight_decay);
+
 #ifdef __cplusplus
 }
 #endif

@@ -440,3 +440,206 @@ def layers_to_text(layers, name="MWVC_Model") -> str:
             parts.append("Sigmoid_Activation")
         parts.append("")
     return "\n".join(parts) + "\n"
+
+
+# ---- training path -------------------------------------------------------------------
+TRAIN_REF_SO = HERE / "_ref" / "libgnntrainref.so"
+TRAIN_DROPIN_SO = HERE / "_ref" / "libgnntraindropin.so"
+
+
+def build_train_harness() -> tuple[Path | None, Path | None]:
+    """oracle/_ref/libgnntrainref.so (the reference's old_files/src/lib/gnn_training.cpp, unmodified) and
+    libgnntraindropin.so (the drop-in host units), both behind oracle/train_harness.cpp."""
+    if Path("/root/reference/old_files/src/lib/gnn_training.cpp").exists():
+        subprocess.check_call(["make", "-s", "-C", str(HERE), "train_ref", "train_dropin"])
+    return (TRAIN_REF_SO if TRAIN_REF_SO.exists() else None, TRAIN_DROPIN_SO if TRAIN_DROPIN_SO.exists() else None)
+
+
+class TrainHarness:
+    """The reference's training interface (old_files/include/gnn/gnn_training.hpp) through
+    oracle/train_harness.cpp: over the reference's own sources (default) or over the drop-in (`dropin=True`)."""
+
+    def __init__(self, dropin: bool = False, threads: int | None = 1):
+        so = TRAIN_DROPIN_SO if dropin else TRAIN_REF_SO
+        if not so.exists():
+            raise FileNotFoundError(f"{so} missing: run `make -C oracle train_ref train_dropin` where /root/reference exists")
+        if not dropin:
+            os.environ.setdefault("OPENBLAS_CORETYPE", "Prescott")     # the kernel set the checker is pinned to (App. B)
+        L = C.CDLL(str(so))
+        pp = C.POINTER(C.POINTER(C.c_float))
+        L.trn_create.restype = C.c_void_p
+        L.trn_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), pp, pp, _f32p, C.POINTER(C.c_size_t)]
+        L.trn_parse.restype = C.c_void_p
+        L.trn_parse.argtypes = [C.c_char_p]
+        L.trn_destroy.argtypes = [C.c_void_p]
+        L.trn_text.restype = C.c_size_t
+        L.trn_text.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.trn_set_graph.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, _u32p, _u32p, _u32p]
+        L.trn_predict.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int]
+        L.trn_backprop.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p]
+        L.trn_mse_step.restype = C.c_float
+        L.trn_mse_step.argtypes = [C.c_void_p, _f32p, C.c_int]
+        L.trn_sgd_step.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_float]
+        L.trn_zero_grad.argtypes = [C.c_void_p]
+        L.trn_read.restype = C.c_size_t
+        L.trn_read.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, _f32p]
+        L.trn_linear_layer.argtypes = [C.c_size_t, C.c_int, C.c_int] + [_f32p] * 8
+        L.trn_graph_layer.argtypes = [C.c_void_p, C.c_int, C.c_float] + [_f32p] * 4
+        L.trn_activation.argtypes = [C.c_int, C.c_size_t] + [_f32p] * 4
+        L.trn_mse.restype = C.c_float
+        L.trn_mse.argtypes = [C.c_size_t, C.c_int, _f32p, _f32p, _f32p]
+        L.trn_blas_threads.argtypes = [C.c_int]
+        if threads:
+            L.trn_blas_threads(threads)
+        self.L = L
+
+    def create(self, layers, scales=None, seeds=None):
+        """layers: [(kind, W | (rows, cols), bias | None)]; linear layers without W keep the seeded random init."""
+        n = len(layers)
+        kinds = (C.c_int * n)(*[int(k) for k, _, _ in layers])
+        rows, cols = (C.c_int * n)(), (C.c_int * n)()
+        Wp, bp = (C.POINTER(C.c_float) * n)(), (C.POINTER(C.c_float) * n)()
+        keep = []
+        for i, (k, W, b) in enumerate(layers):
+            if k != LINEAR:
+                continue
+            if isinstance(W, tuple):
+                rows[i], cols[i] = W
+                continue
+            W = np.ascontiguousarray(W, np.float32)
+            b = np.ascontiguousarray(b, np.float32).ravel()
+            rows[i], cols[i] = W.shape
+            keep += [W, b]
+            Wp[i], bp[i] = _p(W, _f32p), _p(b, _f32p)
+        sc = np.ascontiguousarray(scales if scales is not None else np.full(n, 1200.0), np.float32)
+        sd = (C.c_size_t * n)(*[int(s) for s in (seeds if seeds is not None else range(n))])
+        h = self.L.trn_create(n, kinds, rows, cols, Wp, bp, _p(sc, _f32p), sd)
+        self._shapes = {i: (int(rows[i]), int(cols[i])) for i in range(n) if layers[i][0] == LINEAR}
+        return h
+
+    def parse(self, text: str):
+        return self.L.trn_parse(text.encode())
+
+    def destroy(self, h):
+        self.L.trn_destroy(h)
+
+    def text(self, h) -> str:
+        n = self.L.trn_text(h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.trn_text(h, buf, n + 1)
+        return buf.value.decode()
+
+    def set_graph(self, h, n, eu, ev, W):
+        eu, ev, W = (np.ascontiguousarray(a, np.uint32) for a in (eu, ev, W))
+        self._n = n
+        self.L.trn_set_graph(h, n, len(eu), _p(eu, _u32p), _p(ev, _u32p), _p(W, _u32p))
+
+    def predict(self, h, x, out_w=1):
+        x = np.ascontiguousarray(x, np.float32).reshape(self._n, -1)
+        out = np.empty((self._n, out_w), np.float32)
+        rc = self.L.trn_predict(h, _p(x, _f32p), x.shape[1], _p(out, _f32p), out_w)
+        if rc:
+            raise RuntimeError("predict left another shape")
+        return out
+
+    def backprop(self, h, grad, in_w=1):
+        grad = np.ascontiguousarray(grad, np.float32).reshape(self._n, -1)
+        gx = np.empty((self._n, in_w), np.float32)
+        w = self.L.trn_backprop(h, _p(grad, _f32p), grad.shape[1], _p(gx, _f32p))
+        assert w == in_w, (w, in_w)
+        return gx
+
+    def mse_step(self, h, y):
+        y = np.ascontiguousarray(y, np.float32).reshape(self._n, -1)
+        return float(self.L.trn_mse_step(h, _p(y, _f32p), y.shape[1]))
+
+    def sgd_step(self, h, batch, lr=0.1, momentum=0.9, wd=0.0):
+        self.L.trn_sgd_step(h, batch, lr, momentum, wd)
+
+    def zero_grad(self, h):
+        self.L.trn_zero_grad(h)
+
+    def read(self, h, what, layer, shape):
+        W, b = np.zeros(shape, np.float32), np.zeros(shape[1], np.float32)
+        k = self.L.trn_read(h, what, layer, _p(W, _f32p), _p(b, _f32p))
+        return (W, b) if k else (None, None)
+
+    def linear_layer(self, W, bias, x, grad):
+        W, x, grad = (np.ascontiguousarray(a, np.float32) for a in (W, x, grad))
+        bias = np.ascontiguousarray(bias, np.float32).ravel()
+        n, (K, N) = x.shape[0], W.shape
+        out, gW, gb, gi = np.empty((n, N), np.float32), np.empty((K, N), np.float32), np.empty(N, np.float32), np.empty((n, K), np.float32)
+        self.L.trn_linear_layer(n, K, N, *(_p(a, _f32p) for a in (W, bias, x, grad, out, gW, gb, gi)))
+        return out, gW, gb, gi
+
+    def graph_layer(self, h, x, grad, scale):
+        x, grad = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(grad, np.float32)
+        w = x.shape[1]
+        out, gi = np.empty((self._n, 2 * w + 3), np.float32), np.empty((self._n, w), np.float32)
+        self.L.trn_graph_layer(h, w, scale, *(_p(a, _f32p) for a in (x, grad, out, gi)))
+        return out, gi
+
+    def activation(self, kind, z, grad):
+        z, grad = np.ascontiguousarray(z, np.float32).ravel(), np.ascontiguousarray(grad, np.float32).ravel()
+        out, gi = np.empty_like(z), np.empty_like(z)
+        self.L.trn_activation(kind, z.size, *(_p(a, _f32p) for a in (z, grad, out, gi)))
+        return out, gi
+
+    def mse(self, x, y):
+        x, y = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(y, np.float32)
+        g = np.empty_like(x)
+        loss = self.L.trn_mse(x.shape[0], x.shape[1], _p(x, _f32p), _p(y, _f32p), _p(g, _f32p))
+        return float(loss), g
+
+
+def train_backward_numpy(layers, scales, row_ptr, col, W, NW, x, grad_out, dtype=np.float64):
+    """CPU restatement of model_training::predict + ::backprop (old_files/src/lib/gnn_training.cpp:17-129) in
+    numpy -- TEST INFRASTRUCTURE.  Forward and backward in `dtype` (float64: what the fp32 results are
+    compared with under a tolerance; the fp32 forward itself is checked bit for bit elsewhere).
+    Returns (out, grad_x, {layer index: (grad_W, grad_bias)})."""
+    n = len(row_ptr) - 1
+    deg = np.diff(row_ptr).astype(np.int64)
+    src = np.repeat(np.arange(n), deg)                        # row of every adjacency entry
+    a = np.asarray(x, dtype).reshape(n, -1)
+    saved = []
+    gi = 0
+    for kind, Wm, b in layers:
+        saved.append(a)
+        if kind == LINEAR:
+            a = a @ np.asarray(Wm, dtype) + np.asarray(b, dtype).reshape(1, -1)
+        elif kind == GRAPH:
+            w = a.shape[1]
+            s = dtype(np.float32(scales[min(gi, len(scales) - 1)]))
+            gi += 1
+            out = np.zeros((n, 2 * w + 3), dtype)
+            np.add.at(out[:, :w], src, a[col])                # :33-36
+            out[:, w:2 * w] = a                               # :37
+            out[:, w + 1] = deg                               # :38-40 (the column quirk, SURVEY.md A.2)
+            out[:, w + 2] = W.astype(dtype) / s
+            out[:, w + 3] = NW.astype(dtype) / s
+            a = out
+        elif kind == RELU:
+            a = np.maximum(a, 0)
+        else:
+            a = 1.0 / (1.0 + np.exp(-a))
+    out = a
+    g = np.asarray(grad_out, dtype).reshape(n, -1)
+    grads = {}
+    for i in range(len(layers) - 1, -1, -1):
+        kind, Wm, b = layers[i]
+        z = saved[i]
+        if kind == LINEAR:
+            grads[i] = (z.T @ g, g.sum(axis=0))               # :19-22
+            g = g @ np.asarray(Wm, dtype).T                   # :25
+        elif kind == GRAPH:
+            w = z.shape[1]
+            gn = np.zeros((n, w), dtype)
+            np.add.at(gn, src, g[col][:, :w])                 # :36-39: grad_out[u] += grad_in[v][0..w) over v in N(u)
+            gn += g[:, w:2 * w]                               # :40
+            g = gn
+        elif kind == RELU:
+            g = np.where(z >= 0, g, 0)                        # :52
+        else:
+            f = 1.0 / (1.0 + np.exp(-z))
+            g = f * (1.0 - f) * g                             # :64
+    return out, g, grads

@@ -239,9 +239,31 @@ __device__ __forceinline__ void named_bar_arrive(int id, int threads) {
 // ---- dense: one layer + bias + ReLU over the warp's tile, in place ----------------
 // T: k-major tile, T[k * kTileStride + i], i = vertex in tile.  Lane (og, vg)
 // owns vertices 4vg..4vg+3 and outputs C*og..C*og+C-1.
+//
+// Zero rows.  The trained network is mostly ReLU-dead: measured with the GNN_VC model, 43-73 % of the
+// (tile, k) pairs of the 32-wide layers hold an activation that is exactly zero for ALL 32 vertices of
+// the tile (6-19 units per layer are zero for every vertex of a graph, the sums of isolated vertices are
+// zero, and the vertices of a tile are alike: they are sorted by degree) -- 55 % of all multiply-adds on
+// the R-MAT benchmark graph, 49 % on the grid.  Such a k adds +-0 to every accumulator, and an
+// accumulator that starts at +0.0 is never -0.0 (RN: x + y = -0 only for x = y = -0), so leaving the
+// step out changes no bit (weights are finite: detect_fused).  `mask` has bit k set when row k of the
+// tile holds a non-zero (or NaN) value; the k loop visits the set bits in ascending order, which is the
+// reference's order for the terms that remain.  The mask of a layer's OUTPUT is collected in its
+// epilogue with one ballot per column group; that of a tile fresh from the gather by tile_row_mask.
+__device__ __forceinline__ uint32_t tile_row_mask(const float *__restrict__ T, int lane) {
+    const uint4 *row = reinterpret_cast<const uint4 *>(T + lane * kTileStride);      // lane = k
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < kTileVerts / 4; ++j) {
+        const uint4 v = row[j];
+        any |= v.x | v.y | v.z | v.w;
+    }
+    return __ballot_sync(0xffffffffu, (any & 0x7FFFFFFFu) != 0u);                    // -0.0 counts as zero
+}
+
 template <int K, int NOUT, bool EXACT>
-__device__ __forceinline__ void tile_linear_relu(float *__restrict__ T, const float *__restrict__ Wsm,
-                                                 const float *__restrict__ bsm, int lane) {
+__device__ __forceinline__ uint32_t tile_linear_relu(float *__restrict__ T, const float *__restrict__ Wsm,
+                                                     const float *__restrict__ bsm, int lane, uint32_t mask) {
     constexpr int C = NOUT / 4;
     static_assert(C == 8 || C == 4, "NOUT must be 32 or 16");
     const int og = lane >> 3, vg = lane & 7;
@@ -251,8 +273,13 @@ __device__ __forceinline__ void tile_linear_relu(float *__restrict__ T, const fl
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[r][c] = 0.0f;
 
-#pragma unroll kDenseUnroll
-    for (int k = 0; k < K; ++k) {
+    // (Software-pipelining this loop by hand -- two operand sets alternating -- made ptxas spill in the gather
+    // loops of the kernel, 236-420 bytes; the other warps of the scheduler cover the shared-memory latency.)
+    uint32_t m = K >= 32 ? mask : (mask & ((1u << (K & 31)) - 1u));
+#pragma unroll 1
+    while (m) {
+        const int k = __ffs((int)m) - 1;
+        m &= m - 1u;
         const float4 a = *reinterpret_cast<const float4 *>(T + k * kTileStride + 4 * vg);
         float w[C];
 #pragma unroll
@@ -267,6 +294,7 @@ __device__ __forceinline__ void tile_linear_relu(float *__restrict__ T, const fl
             for (int c = 0; c < C; ++c) acc[r][c] = mac<EXACT>(av[r], w[c], acc[r][c]);
     }
     __syncwarp();   // every lane is done reading the input tile
+    uint32_t out_mask = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const float b = bsm[C * og + c];
@@ -276,8 +304,14 @@ __device__ __forceinline__ void tile_linear_relu(float *__restrict__ T, const fl
         o.z = relu_ref(__fadd_rn(acc[2][c], b));
         o.w = relu_ref(__fadd_rn(acc[3][c], b));
         *reinterpret_cast<float4 *>(T + (C * og + c) * kTileStride + 4 * vg) = o;
+        // output column C * og' + c is non-zero somewhere in the tile iff one of the lanes 8 og' .. 8 og' + 7 says so
+        const uint32_t nz = __ballot_sync(0xffffffffu, !(o.x == 0.0f && o.y == 0.0f && o.z == 0.0f && o.w == 0.0f));
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            if ((nz >> (8 * g)) & 0xFFu) out_mask |= 1u << (C * g + c);
     }
     __syncwarp();
+    return out_mask;
 }
 
 // Last dense layer of stages 0/1 (K=32 -> 16) + bias + ReLU, stored straight
@@ -289,15 +323,19 @@ __device__ __forceinline__ void tile_linear_relu_store16(const float *__restrict
                                                          float *__restrict__ out /* global row 0 */,
                                                          const uint32_t *__restrict__ vid /* smem: global vertex id per slot */,
                                                          int valid /* slots of the tile that hold a vertex */,
-                                                         const PeerOut &peers, int live /* leading slots other ranks read */) {
+                                                         const PeerOut &peers, int live /* leading slots other ranks read */,
+                                                         uint32_t mask /* non-zero rows of T, see tile_linear_relu */) {
     const int og = lane >> 3, vg = lane & 7;
     float acc[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
-#pragma unroll kDenseUnroll
-    for (int k = 0; k < K; ++k) {
+    uint32_t m = K >= 32 ? mask : (mask & ((1u << (K & 31)) - 1u));
+#pragma unroll 1
+    while (m) {
+        const int k = __ffs((int)m) - 1;
+        m &= m - 1u;
         const float4 a = *reinterpret_cast<const float4 *>(T + k * kTileStride + 4 * vg);
         const float4 ww = *reinterpret_cast<const float4 *>(Wsm + k * 16 + 4 * og);
         const float av[4] = {a.x, a.y, a.z, a.w};
@@ -493,10 +531,11 @@ __device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const u
         __syncwarp();
         return;
     }
-    tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane);
-    tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane);
+    uint32_t rows = D.Ka >= 32 ? tile_row_mask(T, lane) : 0xFFFFFFFFu;       // the 5 features of stage 0: not worth a pass
+    rows = tile_linear_relu<D.Ka, D.Na, EXACT>(T, Wa, ba, lane, rows);
+    rows = tile_linear_relu<D.Kb, D.Nb, EXACT>(T, Wb, bb, lane, rows);
     if constexpr (STAGE < 2) {
-        tile_linear_relu_store16<D.Kc, EXACT>(T, Wc, bc, lane, out, vid, count, peers, live);
+        tile_linear_relu_store16<D.Kc, EXACT>(T, Wc, bc, lane, out, vid, count, peers, live, rows);
     } else {
         // 16 -> 1: one lane per vertex.  OpenBLAS' 1-column kernel: even/odd
         // accumulators, C = even + odd (oracle/gnn_oracle.c dot_two_acc).

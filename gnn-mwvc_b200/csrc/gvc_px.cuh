@@ -397,6 +397,14 @@ __device__ __forceinline__ void px_prefetch_batch16(const float4 *__restrict__ r
 //     (else the quad is redone batch by batch, which is always right);
 //   * the rows of the next batch flagged dirty by phase B are prefetched into L1 as soon as it is known to
 //     be next, i.e. while the clean batches before it are walked.
+// With this the 262 144-neighbour star walks at 119-138 cycles per clean batch (stage 2: 0.52 -> 0.41 ms), and
+// the shard of an 8-GPU run that owns the 258 306-neighbour hub of R-MAT scale 23 takes 0.75 / 0.72 ms for
+// stages 1 / 2 instead of 0.86 / 0.83 (tools/shard_probe.py; fast mode, which may split the sum: 0.55 / 0.50).
+// Tried and measured slower (profiles/r2_walk_variants.json): a ring of record words in registers, sixteen
+// batches ahead, P / D by shuffle -- next to a call ptxas keeps the ring in local memory, and a load that is
+// stored straight to the stack is waited for at once (0.88 / 0.83); eight batches per vote with the records
+// of eight batches in shared memory (0.84 / 0.81): the walk is bound by the instructions per batch that one
+// warp gets issued next to three busy ones, not by a fixed cost per vote.
 __device__ __noinline__ float px_walk16(const PxArgs &px, uint32_t g, uint32_t deg, float *__restrict__ T, int lane) {
     const uint2 hi = __ldg(px.info + g);
     const long long t_in = clock64();

@@ -109,7 +109,7 @@ def test_trainer_on_a_larger_graph_fast_matches_exact_and_float64(ctx):
     """65 536 vertices / 1 M edges: fast against exact, and both against the float64 restatement"""
     g = graphs.rmat_graph(16, 16, seed=21)
     row_ptr, col, W, NW, x, s = inputs_of(g)
-    layers = po.random_model(5)
+    layers = capi.random_model(5)
     ctx.graph_upload(row_ptr, col, W, NW)
     rng = np.random.default_rng(3)
     y = (rng.random((g.n, 1)) < 0.5).astype(np.float32)

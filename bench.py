@@ -490,9 +490,9 @@ def run_ours(args):
                 e2e = {"value": max(e_total, 1) / pred_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * m + 16 * n + 4 * n),
                        "d2h_bytes_per_step": int(4 * n), "ms_per_step": pred_s * 1e3, "first_call_ms": first * 1e3,
                        "what": "gnn::model::predict(in, out, reduction_graph) through the reference's C++ interface "
-                               "(host/gvc_dropin_capi.cpp), per step: adjacency read from the reduction_graph, staged "
-                               "through pinned memory and uploaded (ids + per-vertex ranges, weights), CSR compaction, "
-                               "checks and degree schedule on the device, H2D of x, 3 fused kernels, D2H of the scores "
+                               "(host/gvc_dropin_capi.cpp), per step: adjacency read from the reduction_graph through begin(u)/end(u), "
+                               "streamed through a ring of pinned slots (edge span + per-vertex ranges, weights, x), packed CSR, "
+                               "checks and degree schedule built on the device, 3 fused kernels, D2H of the scores "
                                "into the host matrix; wall clock of predict()",
                        "c_abi": c_abi, "csr_resident": resident}
                 dr.graph_destroy(dg)
@@ -584,7 +584,7 @@ def run_ours(args):
             traffic = None
             tp = ROOT / "profiles" / "traffic.json"
             if tp.exists():
-                traffic = json.loads(tp.read_text()).get(f"stage1_{args.mode}")
+                traffic = json.loads(tp.read_text()).get(wl_name, {}).get(f"stage1_{args.mode}")   # ncu, per launch, this workload
             roof = {"bound": "hbm", "kernel": f"stage_kernel<1,{args.mode}> (graph layer w=16 + 35->32->32->16)",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": b1,

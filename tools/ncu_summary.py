@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Condense an ncu report of the stage kernels into profiles/: key metrics per kernel
 (profiles/<name>.json) and DRAM bytes per launch (profiles/traffic.json, read by bench.py).
-usage: python tools/ncu_summary.py gpurun_out/prof_X.ncu-rep profiles/r1_ncu_stage_kernels_X.json [exact|fast]"""
+usage: python tools/ncu_summary.py gpurun_out/prof_X.ncu-rep profiles/r2_ncu_stage_kernels_X.json [exact|fast] [workload name of the bench line, default rmat_scale20_ef16] [bench arguments, for the record]"""
 import csv
 import io
 import json
@@ -21,6 +21,8 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
 rep, out = sys.argv[1], sys.argv[2]
 mode = sys.argv[3] if len(sys.argv) > 3 else "exact"
+workload = sys.argv[4] if len(sys.argv) > 4 else "rmat_scale20_ef16"
+bench_args = sys.argv[5] if len(sys.argv) > 5 else ""
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -35,7 +37,8 @@ for r in data:
     kernels.append(k)
 Path(out).write_text(json.dumps({
     "source": "ncu --set full --clock-control none --import-source on -k regex:stage_kernel -s 9 -c 3 python bench.py "
-              "--steps 2 --warmup 3 --no-cpu-baseline (the .ncu-rep stays in gpurun_out/)",
+              "--steps 2 --warmup 3 --no-cpu-baseline " + bench_args + " (the .ncu-rep stays in gpurun_out/)",
+    "workload": workload,
     "note": "one kernel at a time, cold L2 after the bench's 256 MiB flush; durations are not bench values",
     "kernels": kernels}, indent=1))
 
@@ -47,8 +50,9 @@ def to_bytes(cell):
 
 tp = ROOT / "profiles" / "traffic.json"
 traffic = json.loads(tp.read_text()) if tp.exists() else {}
+traffic = {k: v for k, v in traffic.items() if isinstance(v, dict)}          # keyed by workload since round 2
 for st, k in enumerate(kernels[:3]):
-    traffic[f"stage{st}_{mode}"] = int(to_bytes(k["dram__bytes_read.sum"]) + to_bytes(k["dram__bytes_write.sum"]))
+    traffic.setdefault(workload, {})[f"stage{st}_{mode}"] = int(to_bytes(k["dram__bytes_read.sum"]) + to_bytes(k["dram__bytes_write.sum"]))
 tp.write_text(json.dumps(traffic, indent=1))
 for k in kernels:
     print(k["kernel"][:40], k["gpu__time_duration.sum"]["value"], "us  dram",

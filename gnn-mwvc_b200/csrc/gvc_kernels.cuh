@@ -445,38 +445,47 @@ __device__ __forceinline__ void tile_linear_relu_mma(float *__restrict__ T, cons
     __syncwarp();
 }
 
-// last layer of stages 0/1 (K = 32 -> 16) + bias + ReLU, stored straight from the accumulator fragments
+// last layer of stages 0/1 (K = 32 -> 16) + bias + ReLU.  The accumulator fragments hold two outputs of two rows
+// per lane; stored from there, an instruction writes 32 contiguous bytes per row -- fine for local memory, but the
+// rows also go to the other GPUs' buffers, and over NVLink half-row writes cost the 8-GPU fast mode 0.3 ms per
+// stage (measured: stage 0 at 0.63 ms against 0.27 ms without peers).  So the 32 x 16 outputs make a round trip
+// through the warp's tile buffer (free once every lane has read its A fragments) and leave as whole 64-byte rows,
+// four lanes per row, exactly like the exact path's epilogue.
 template <int K>
-__device__ __forceinline__ void tile_linear_relu_store16_mma(const float *__restrict__ T, const float *__restrict__ Wf,
+__device__ __forceinline__ void tile_linear_relu_store16_mma(float *__restrict__ T, const float *__restrict__ Wf,
                                                              const float *__restrict__ bsm, int lane, float *__restrict__ out,
                                                              const uint32_t *__restrict__ vid, int valid, const PeerOut &peers,
                                                              int live) {
     float acc[2][2][4];
     tile_mma<K, 16>(T, Wf, lane, acc);
+    __syncwarp();                                    // every lane is done reading the input tile
     const int r = lane >> 2, c = lane & 3;
-    // A lane holds outputs (2c, 2c + 1) of rows r and r + 8; it trades one of the pairs with its neighbour
-    // (lane ^ 1) so that even lanes end up with four consecutive outputs of row r and odd lanes with four of
-    // row r + 8: 128-bit stores, to the local buffer and over NVLink alike.
+    constexpr int kRow = 16;                         // floats per staged row (128-bit reads conflict-free, 64-bit writes two-way)
 #pragma unroll
-    for (int mb = 0; mb < 2; ++mb) {
-        const int i = 16 * mb + r + ((c & 1) ? 8 : 0);
-        const bool on = i < valid;
-        const uint32_t v = on ? vid[i] : 0u;
-        const uint32_t m = (on && i < live) ? (peers.mask ? peers.mask[v] : 0xFFu) : 0u;
+    for (int nb = 0; nb < 2; ++nb) {
+        const float b0 = bsm[8 * nb + 2 * c], b1 = bsm[8 * nb + 2 * c + 1];
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-            const float b0 = bsm[8 * nb + 2 * c], b1 = bsm[8 * nb + 2 * c + 1];
-            const float lo0 = relu_ref(acc[mb][nb][0] + b0), lo1 = relu_ref(acc[mb][nb][1] + b1);     // row r
-            const float hi0 = relu_ref(acc[mb][nb][2] + b0), hi1 = relu_ref(acc[mb][nb][3] + b1);     // row r + 8
-            const float sx = (c & 1) ? lo0 : hi0, sy = (c & 1) ? lo1 : hi1;                          // what the neighbour wants
-            const float gx = __shfl_xor_sync(0xffffffffu, sx, 1), gy = __shfl_xor_sync(0xffffffffu, sy, 1);
-            const float4 o = (c & 1) ? make_float4(gx, gy, hi0, hi1) : make_float4(lo0, lo1, gx, gy);
-            if (on) {
-                const size_t at = (size_t)v * 16 + 8 * nb + 4 * (c >> 1);
-                *reinterpret_cast<float4 *>(out + at) = o;
+        for (int mb = 0; mb < 2; ++mb) {
+            float *t = T + (16 * mb + r) * kRow + 8 * nb + 2 * c;
+            *reinterpret_cast<float2 *>(t) = make_float2(relu_ref(acc[mb][nb][0] + b0), relu_ref(acc[mb][nb][1] + b1));
+            *reinterpret_cast<float2 *>(t + 8 * kRow) = make_float2(relu_ref(acc[mb][nb][2] + b0), relu_ref(acc[mb][nb][3] + b1));
+        }
+    }
+    __syncwarp();
+    const int sv = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int i = 8 * p + sv;
+        if (i < valid) {
+            const float4 o = *reinterpret_cast<const float4 *>(T + i * kRow + 4 * q);
+            const uint32_t v = vid[i];
+            const size_t at = (size_t)v * 16 + 4 * q;
+            *reinterpret_cast<float4 *>(out + at) = o;
+            if (i < live) {
+                const uint32_t m = peers.mask ? peers.mask[v] : 0xFFu;
 #pragma unroll 1
-                for (int q = 0; q < peers.n; ++q)
-                    if (m >> q & 1u) *reinterpret_cast<float4 *>(peers.p[q] + at) = o;
+                for (int g = 0; g < peers.n; ++g)
+                    if (m >> g & 1u) *reinterpret_cast<float4 *>(peers.p[g] + at) = o;
             }
         }
     }
@@ -516,7 +525,7 @@ __device__ __noinline__ void tile_dense_and_store(float *__restrict__ T, const u
         tile_linear_relu_mma<D.Ka, D.Na>(T, Fa, fa, lane);
         tile_linear_relu_mma<D.Kb, D.Nb>(T, Fb, fb, lane);
         if constexpr (STAGE < 2) {
-            tile_linear_relu_store16_mma<D.Kc>(T, Fc, Fc + mma_layer_floats(D.Kc, D.Nc), lane, out, vid, count, peers, live);
+            tile_linear_relu_store16_mma<D.Kc>(T, Fc, Fc + mma_layer_floats(D.Kc, D.Nc), lane, out, vid, count, peers, live);   // T is scratch from here on
         } else {
             const float *Wc1 = Fc, *bc1 = Fc + D.Kc * D.Nc;
             float s = 0.0f;

@@ -431,7 +431,10 @@ __device__ __noinline__ float px_walk16(const PxArgs &px, uint32_t g, uint32_t d
         if (q0 < nq) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec_lines + (size_t)q0 * 128));
     };
     prefetch_quads(0); prefetch_quads(8); prefetch_quads(16);
-    float4 rnext = rec4[0];
+    // four quads of records in flight in four named registers (no array: next to the calls below ptxas would
+    // put one into local memory): the load issued now is consumed four iterations later
+    float4 rnext = rec4[0], rn2 = rec4[(size_t)min(1u, nq - 1) * 32], rn3 = rec4[(size_t)min(2u, nq - 1) * 32],
+           rn4 = rec4[(size_t)min(3u, nq - 1) * 32];
     // dirty: bit i = batch (32-block base) + i was flagged by phase B; the next block's flags are in flight
     uint32_t dirty = 0, fl_next = F[min((uint32_t)lane, nb - 1)];
     uint32_t pre_b = 0xFFFFFFFFu;                                    // the batch whose rows were requested ahead (L1 prefetch)
@@ -444,7 +447,8 @@ __device__ __noinline__ float px_walk16(const PxArgs &px, uint32_t g, uint32_t d
         }
         __syncwarp();
         reinterpret_cast<float4 *>(R)[lane] = rnext;
-        rnext = rec4[(size_t)min(qd + 1, nq - 1) * 32];
+        rnext = rn2; rn2 = rn3; rn3 = rn4;
+        rn4 = rec4[(size_t)min(qd + 4, nq - 1) * 32];
         // the next dirty batch of this 32-block at or after this quad: get its rows under way
         const uint32_t ahead = dirty >> ((4 * qd) & 31u);
         if (ahead != 0u && pre_b == 0xFFFFFFFFu) {

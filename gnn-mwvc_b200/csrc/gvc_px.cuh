@@ -404,7 +404,10 @@ __device__ __forceinline__ void px_prefetch_batch16(const float4 *__restrict__ r
 // batches ahead, P / D by shuffle -- next to a call ptxas keeps the ring in local memory, and a load that is
 // stored straight to the stack is waited for at once (0.88 / 0.83); eight batches per vote with the records
 // of eight batches in shared memory (0.84 / 0.81): the walk is bound by the instructions per batch that one
-// warp gets issued next to three busy ones, not by a fixed cost per vote.
+// warp gets issued next to three busy ones, not by a fixed cost per vote; four quads of records in flight in
+// four named registers instead of one (1.03 / 1.01, and the whole scale-20 forward 1.13 -> 1.25 ms); the walk
+// organised in blocks of 32 batches with the flag bookkeeping hoisted out of the quad loop (0.68 / 0.64 on that
+// shard -- the best walk -- but the single-GPU scale-20 forward 1.13 -> 1.19 ms: more spills in the stage kernels).
 __device__ __noinline__ float px_walk16(const PxArgs &px, uint32_t g, uint32_t deg, float *__restrict__ T, int lane) {
     const uint2 hi = __ldg(px.info + g);
     const long long t_in = clock64();
@@ -431,10 +434,7 @@ __device__ __noinline__ float px_walk16(const PxArgs &px, uint32_t g, uint32_t d
         if (q0 < nq) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec_lines + (size_t)q0 * 128));
     };
     prefetch_quads(0); prefetch_quads(8); prefetch_quads(16);
-    // four quads of records in flight in four named registers (no array: next to the calls below ptxas would
-    // put one into local memory): the load issued now is consumed four iterations later
-    float4 rnext = rec4[0], rn2 = rec4[(size_t)min(1u, nq - 1) * 32], rn3 = rec4[(size_t)min(2u, nq - 1) * 32],
-           rn4 = rec4[(size_t)min(3u, nq - 1) * 32];
+    float4 rnext = rec4[0];
     // dirty: bit i = batch (32-block base) + i was flagged by phase B; the next block's flags are in flight
     uint32_t dirty = 0, fl_next = F[min((uint32_t)lane, nb - 1)];
     uint32_t pre_b = 0xFFFFFFFFu;                                    // the batch whose rows were requested ahead (L1 prefetch)
@@ -447,8 +447,7 @@ __device__ __noinline__ float px_walk16(const PxArgs &px, uint32_t g, uint32_t d
         }
         __syncwarp();
         reinterpret_cast<float4 *>(R)[lane] = rnext;
-        rnext = rn2; rn2 = rn3; rn3 = rn4;
-        rn4 = rec4[(size_t)min(qd + 4, nq - 1) * 32];
+        rnext = rec4[(size_t)min(qd + 1, nq - 1) * 32];
         // the next dirty batch of this 32-block at or after this quad: get its rows under way
         const uint32_t ahead = dirty >> ((4 * qd) & 31u);
         if (ahead != 0u && pre_b == 0xFFFFFFFFu) {

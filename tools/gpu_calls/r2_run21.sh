@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for tag in base walk8; do
+for tag in base walk9; do
   if [ $tag = base ]; then unset GVC_LIB; else export GVC_LIB=$PWD/gnn-mwvc_b200/_variants/libgvc_$tag.so; fi
   echo "== $tag"
   timeout 900 python -m pytest tests -m gpu -x -q -k "parallel_exact or bench_size or degree_ladder" 2>&1 | tail -2

@@ -1154,19 +1154,22 @@ int gvc_graph_upload_stream_x(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fil
     // (copy + event), and those serialise over all threads: measured at 256 KB per slot on the 146 MB
     // benchmark graph, 544 items kept the copy engine at half of the PCIe rate.  Large graphs therefore
     // use 1 MB slots, small ones 256 KB (more pieces to overlap filling with copying).
+    // Item size: as large as possible (fewer driver calls) while every worker still gets four or more items to
+    // overlap its filling with its copies -- total / (4 x workers), between 64 KB and 1 MB.  (Tying the item size
+    // to the ring's slot size, which never shrinks, left the later, smaller graphs of a solver run with 2-6
+    // workers: ER 1M / 5M, second predict, 22 items of 1 MB on 6 threads.)  GVC_SLOT_KB overrides.
     static const size_t env_slot_kb = [] { const char *e = std::getenv("GVC_SLOT_KB"); return e ? (size_t)std::strtoull(e, nullptr, 10) : 0; }();
+    static const int env_threads = [] { const char *e = std::getenv("GVC_UPLOAD_THREADS"); return e ? std::atoi(e) : 0; }();
+    const int want_workers = n_threads > 0 ? n_threads : env_threads > 0 ? env_threads
+                                           : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
     const uint64_t total_bytes = 20ull * n + 4ull * span_len;
-    size_t slot_bytes = env_slot_kb ? (env_slot_kb << 10) : total_bytes >= (32ull << 20) ? ((size_t)1 << 20) : ((size_t)256 << 10);
-    slot_bytes = std::max<size_t>(64u << 10, (slot_bytes + 4095) & ~(size_t)4095);
-    slot_bytes = std::max(slot_bytes, c->slot_bytes);            // an existing ring is never shrunk
-    const uint32_t v_chunk = (uint32_t)(slot_bytes / 20 / 1024 * 1024);           // 5 arrays per slot
+    size_t slot_bytes = env_slot_kb ? (env_slot_kb << 10) : (size_t)std::min<uint64_t>(1u << 20, total_bytes / (4ull * want_workers));
+    slot_bytes = std::max<size_t>(64u << 10, (slot_bytes + 65535) & ~(size_t)65535);
+    const uint32_t v_chunk = (uint32_t)(slot_bytes / 20 / 1024 * 1024);           // 5 arrays per item
     const uint64_t s_chunk = slot_bytes / sizeof(uint32_t);
     const uint64_t n_vchunks = ((uint64_t)n + v_chunk - 1) / v_chunk, n_schunks = (span_len + s_chunk - 1) / s_chunk;
     const uint64_t n_items = n_vchunks + n_schunks;
-    static const int env_threads = [] { const char *e = std::getenv("GVC_UPLOAD_THREADS"); return e ? std::atoi(e) : 0; }();
-    int workers = n_threads > 0 ? n_threads : env_threads > 0 ? env_threads
-                                : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
-    workers = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)workers, (n_items + 3) / 4));   // >= 4 items per thread
+    int workers = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)want_workers, (n_items + 3) / 4));   // >= 4 items per thread
     if ((rc = ensure_ring(c, std::max(2 * workers, 16) / workers * workers, slot_bytes))) return rc;
     arena_hint(c, n, span_len);
     if ((rc = c->d_rb.reserve(n))) return rc;
@@ -1280,7 +1283,7 @@ int gvc_graph_upload_stream_x(gvc_ctx *c, uint32_t n, uint64_t span_len, gvc_fil
     }
     if (tr.on)
         std::fprintf(stderr, "gvc trace: stream: %d workers, %llu items of %zu KB; per worker: wait for a slot %.3f ms, fill %.3f ms, issue %.3f ms\n",
-                     workers, (unsigned long long)n_items, c->slot_bytes >> 10, ns_wait.load() * 1e-6 / workers, ns_fill.load() * 1e-6 / workers,
+                     workers, (unsigned long long)n_items, slot_bytes >> 10, ns_wait.load() * 1e-6 / workers, ns_fill.load() * 1e-6 / workers,
                      ns_issue.load() * 1e-6 / workers);
     if (rc_sched) { cudaStreamSynchronize(c->copy_stream); return rc_sched; }
     tr.tick("stream: offsets + schedule");

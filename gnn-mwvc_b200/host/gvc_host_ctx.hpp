@@ -5,6 +5,8 @@
 //   GVC_DEVICE  CUDA ordinal (default 0)
 //   GVC_MODE    "exact" (default, bit-identical scores) or "fast"
 //   GVC_WARM    0: no early context creation on a helper thread (see warm_start)
+//   GVC_WARM_MB device memory the helper thread allocates up front (default 1024; the first cudaMalloc of a
+//               process took 0.5 - 90 ms on the pool's boxes; 0: none, the first predict allocates what it needs)
 //   GVC_DEVICES "0,1,2,3": predict() shards graphs of at least GVC_MULTI_MIN_VERTICES vertices
 //               (default 2 000 000) over these devices (gvc_group, include/gvc.h); smaller graphs and
 //               everything else stay on the first of them
@@ -46,7 +48,8 @@ inline const std::vector<int> &devices() {
 }
 
 // The context is created at first use -- or ahead of time by warm_start(): CUDA initialisation (a few
-// hundred ms in a fresh process) and the pinning of the upload ring (about 8 ms) then happen on a helper
+// hundred ms in a fresh process), the pinning of the upload ring (about 8 ms) and the first device allocation
+// (0.5 - 90 ms, measured) then happen on a helper
 // thread while the solver still parses and reduces its graph, instead of inside the first predict().
 inline gvc_ctx *context_impl(bool fatal, bool warm) {
     static std::mutex mu;
@@ -61,7 +64,11 @@ inline gvc_ctx *context_impl(bool fatal, bool warm) {
             if (fatal) die("gvc_ctx_create", rc);
             return nullptr;                    // the helper thread leaves the complaint to the call that needs the GPU
         }
-        if (warm) gvc_ctx_warm(c, 0);          // best effort
+        if (warm) {                            // best effort: the pinned ring and a first chunk of device memory
+            const char *mb = std::getenv("GVC_WARM_MB");
+            const unsigned long long warm_mb = mb ? std::strtoull(mb, nullptr, 10) : 1024ull;
+            gvc_ctx_warm(c, warm_mb << 20);
+        }
         ctx = c;
     }
     return ctx;

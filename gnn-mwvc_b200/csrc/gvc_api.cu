@@ -912,7 +912,7 @@ extern "C" {
 
 const char *gvc_last_error(void) { return g_err.c_str(); }
 int gvc_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }   // for the other translation units of libgvc
-int gvc_abi_version(void) { return 3; }
+int gvc_abi_version(void) { return 4; }   // 4: upload_stream_x, ctx_warm, trainer + backward entry points (additive)
 
 int gvc_ctx_create(gvc_ctx **out, int device) {
     if (!out) return fail(GVC_ERR_ARG, "out is null");

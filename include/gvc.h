@@ -52,7 +52,7 @@ enum {
 
 const char *gvc_last_error(void);
 
-/* Version of this ABI (bumped on incompatible change). */
+/* Version of this ABI (bumped when entry points are added or change meaning; 4 = round 2). */
 int gvc_abi_version(void);
 
 /* ---- context ------------------------------------------------------------ */

@@ -66,4 +66,4 @@ def test_fails_loudly_without_gpu(lib):
 
 
 def test_abi_version(lib):
-    assert lib.gvc_abi_version() == 3
+    assert lib.gvc_abi_version() == 4

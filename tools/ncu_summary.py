@@ -18,7 +18,13 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
-        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        # pipe shares (the tensor pipe is what the fast mode's mma.sync layers run on)
+        "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
 rep, out = sys.argv[1], sys.argv[2]
 mode = sys.argv[3] if len(sys.argv) > 3 else "exact"
 workload = sys.argv[4] if len(sys.argv) > 4 else "rmat_scale20_ef16"

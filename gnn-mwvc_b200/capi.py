@@ -525,9 +525,10 @@ class Trainer:
 
     def predict(self, x, scales, mode: int = MODE_EXACT, want_out: bool = True):
         n = self.ctx.n_global
-        x = _np(x, np.float32).reshape(n, -1)
-        if x.shape[1] != self.in_w:
-            raise GvcError(f"x is {x.shape[1]} wide, the model takes {self.in_w}")
+        x = _np(x, np.float32)
+        if x.size != n * self.in_w:
+            raise GvcError(f"x has {x.size} values, the model takes {n} x {self.in_w}")
+        x = x.reshape(n, self.in_w)
         sc = _np(np.atleast_1d(scales), np.float32)
         out = np.empty((n, self.out_w), np.float32) if want_out else None
         self.ctx._check(self.lib.gvc_trainer_predict(self.h, _ptr(x, _f32p), _ptr(sc, _f32p), sc.size,
@@ -536,13 +537,13 @@ class Trainer:
 
     def backprop(self, grad, mode: int = MODE_EXACT, want_grad_x: bool = True):
         n = self.ctx.n_global
-        grad = _np(grad, np.float32).reshape(n, -1)
+        grad = _np(grad, np.float32).reshape(n, self.out_w)
         gx = np.empty((n, self.in_w), np.float32) if want_grad_x else None
         self.ctx._check(self.lib.gvc_trainer_backprop(self.h, _ptr(grad, _f32p), _ptr(gx, _f32p) if want_grad_x else None, mode))
         return gx
 
     def mse_backprop(self, y, mode: int = MODE_EXACT) -> float:
-        y = _np(y, np.float32).reshape(self.ctx.n_global, -1)
+        y = _np(y, np.float32).reshape(self.ctx.n_global, self.out_w)
         loss = C.c_float()
         self.ctx._check(self.lib.gvc_trainer_mse_backprop(self.h, _ptr(y, _f32p), C.cast(C.byref(loss), _f32p), mode))
         return float(loss.value)

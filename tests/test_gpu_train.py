@@ -148,6 +148,36 @@ def test_backprop_needs_a_predict_on_the_current_graph(ctx, z):
     tr.close()
 
 
+def test_trainer_on_an_empty_graph_and_a_generic_model(ctx):
+    """n = 0 is a no-op everywhere (the solver calls predict on an empty graph); a model that is not
+    the GNN_VC architecture (graph layer of width 3, one linear layer, sigmoid) trains through the same kernels"""
+    layers = [(capi.GRAPH, None, None), (capi.LINEAR, np.full((9, 2), 0.1, np.float32), np.zeros(2, np.float32)), (capi.SIGMOID, None, None)]
+    ctx.graph_upload(np.zeros(1, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+    tr = capi.Trainer(ctx, layers)
+    assert (tr.in_w, tr.out_w) == (3, 2)
+    assert tr.predict(np.zeros((0, 3), np.float32), 200.0).shape == (0, 2)
+    assert tr.backprop(np.zeros((0, 2), np.float32)).shape == (0, 3)
+    assert tr.mse_backprop(np.zeros((0, 2), np.float32)) == 0.0
+    g = graphs.er_graph(500, 1500, seed=3)
+    row_ptr, col, W, NW, _, s = inputs_of(g)
+    ctx.graph_upload(row_ptr, col, W, NW)
+    rng = np.random.default_rng(8)
+    x = rng.random((g.n, 3)).astype(np.float32)
+    y = rng.random((g.n, 2)).astype(np.float32)
+    out = tr.predict(x, s)
+    loss = tr.mse_backprop(y)
+    out64, _, _ = po.train_backward_numpy(layers, [s], row_ptr, col, W, NW, x, np.zeros_like(y))
+    _, gx64, g64 = po.train_backward_numpy(layers, [s], row_ptr, col, W, NW, x, (out64 - y))     # MSE_grad: 2 (x - y) / width, width 2
+    assert rel_to_scale(out, out64) < 1e-5
+    assert abs(loss - float(np.mean(np.sum((out64 - y) ** 2, axis=1) / 2))) < 1e-5
+    gW, gb = tr.read(1, 1)
+    assert rel_to_scale(gW, g64[1][0]) < 1e-4 and rel_to_scale(gb, g64[1][1]) < 1e-4
+    tr.predict(x, s)
+    gx = tr.backprop((out64 - y).astype(np.float32))
+    assert rel_to_scale(gx, gx64) < 1e-4
+    tr.close()
+
+
 def test_single_layer_entry_points_vs_the_live_reference(ctx, z):
     if not po.TRAIN_REF_SO.exists():
         pytest.skip("oracle/_ref/libgnntrainref.so did not travel")

@@ -103,6 +103,7 @@ SIGNATURES = {
     "gvc_sync": (C.c_int, [C.c_void_p]),
     "gvc_launch_count": (C.c_uint64, [C.c_void_p]),
     "gvc_debug_h": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "gvc_debug_row_order": (C.c_int, [C.c_void_p, _u32p]),
     "gvc_debug_px": (C.c_int, [C.c_void_p, _u32p]),
 }
 
@@ -343,6 +344,13 @@ class Context:
         self._check(self.lib.gvc_forward_keys(self.h, _ptr(x, _f32p), float(weight_scale), _ptr(out, _f32p), _ptr(keys, _f32p),
                                               side.ctypes.data_as(C.POINTER(C.c_ubyte)), mode))
         return out, keys, side
+
+    def row_order(self) -> np.ndarray:
+        """vertex_of_row: which vertex every row of h1 / h2 belongs to (identity unless renumbered, gvc_debug_row_order)"""
+        out = np.empty(self.n_global, np.uint32)
+        if self.lib.gvc_debug_row_order(self.h, _ptr(out, _u32p)) < 0:
+            raise GvcError("gvc_debug_row_order failed")
+        return out
 
     def forward_device(self, d_x, weight_scale: float, d_scores, mode: int = MODE_EXACT):
         self._check(self.lib.gvc_forward_device(self.h, _dptr(d_x), float(weight_scale), _dptr(d_scores), mode))

@@ -793,7 +793,7 @@ range_compact_kernel(const uint32_t *__restrict__ span, const uint32_t *__restri
 // vertices -- each dragging a cold neighbour's row along.  With the vertices renumbered in the order of the degree
 // schedule the hot rows lie next to each other and L2 holds twice as many of them: measured on that graph
 // (tools/relabel_probe.py) the three stages take 1.74 / 4.23 / 3.92 ms instead of 1.78 / 4.46 / 4.18.
-// So for whole-graph contexts of GVC_ROW_ORDER_MIN_VERTICES (default 2 000 000) vertices and more the fused path
+// So for whole-graph contexts of GVC_ROW_ORDER_MIN_VERTICES (default 500 000) vertices and more the fused path
 // works on an internal copy of the graph in that numbering (built on the device with the streamed upload's
 // kernels: the original adjacency is the "span", the new rows are ranges into it, ids are translated on the
 // way); x is permuted on the way in, scores and selection keys on the way out.  Per-vertex arithmetic and the
@@ -830,7 +830,7 @@ __global__ void rows_scatter_kernel(const T *__restrict__ src, const uint32_t *_
 int relabel_rows(gvc_ctx *c, bool at_upload) {
     if (c->relabelled) return 0;
     const char *env = std::getenv("GVC_ROW_ORDER_MIN_VERTICES");          // read per call: tests switch it
-    const uint64_t min_n = env ? std::strtoull(env, nullptr, 10) : 2000000ull;
+    const uint64_t min_n = env ? std::strtoull(env, nullptr, 10) : 500000ull;
     const char *env_after = std::getenv("GVC_ROW_ORDER_AFTER");
     const uint64_t after = env_after ? std::strtoull(env_after, nullptr, 10) : 1ull;
     if (at_upload ? after != 0 : c->forwards_on_graph < after) return 0;

@@ -319,7 +319,7 @@ int gvc_debug_px(gvc_ctx *ctx, uint32_t *out8);
 /* Device buffers of the last forward (h1/h2: n_global x 16), for tests. */
 /* Rows of the stage outputs h1 / h2 (gvc_stage_device with the caller's buffers, gvc_debug_h): row r belongs to
  * vertex vertex_of_row[r].  The identity, except for whole-graph contexts of GVC_ROW_ORDER_MIN_VERTICES (default
- * 2 000 000) vertices and more, which keep their rows in the order of the degree schedule so that the rows of
+ * 500 000) vertices and more, which keep their rows in the order of the degree schedule so that the rows of
  * the high-degree vertices share cache lines; x, scores and selection keys are always in
  * the caller's numbering.  Returns 1 if renumbered, 0 if not, < 0 on error. */
 int gvc_debug_row_order(gvc_ctx *ctx, uint32_t *vertex_of_row);

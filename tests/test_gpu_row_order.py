@@ -1,4 +1,4 @@
-"""GPU: rows in schedule order (gvc_api.cu relabel_rows).  Whole-graph contexts of 2 M vertices and more run the
+"""GPU: rows in schedule order (gvc_api.cu relabel_rows).  Whole-graph contexts of 500 000 vertices and more run the
 fused path on an internal copy of the graph whose vertices are renumbered by the degree schedule (L2 then holds
 the rows of the hubs without their cold neighbours).  Nothing a caller sees may change: x, scores and selection
 keys stay in the caller's numbering and every bit stays the same.  GVC_ROW_ORDER_MIN_VERTICES=0 forces the
@@ -131,5 +131,28 @@ def test_default_threshold_leaves_small_graphs_alone(ctx):
         ctx.forward(x, s)
         ctx.forward(x, s)
         assert np.array_equal(ctx.row_order(), np.arange(g.n))
+    finally:
+        _setenv(**old)
+
+
+def test_bench_graph_same_bits_before_and_after_the_reordering(ctx):
+    """R-MAT scale 20 (what bench.py times; its first forward is checked against the compiled reference in
+    test_gpu_parity.py): the forwards after the rows were reordered return the very same scores, both modes"""
+    old = _setenv(GVC_ROW_ORDER_MIN_VERTICES=None, GVC_ROW_ORDER_AFTER=None)
+    try:
+        g = graphs.rmat_graph(20, 16, seed=42)
+        rp, col, W, NW, x, s = inputs_of(g)
+        ctx.graph_upload(rp, col, W, NW)
+        first = ctx.forward(x, s)
+        assert np.array_equal(ctx.row_order(), np.arange(g.n))
+        second, keys, side = ctx.forward_keys(x, s)
+        rows = ctx.row_order()
+        assert not np.array_equal(rows, np.arange(g.n)) and np.array_equal(np.sort(rows), np.arange(g.n))
+        assert_bit_equal(second, first, "second forward (rows reordered)")
+        assert_bit_equal(keys, np.minimum(first, np.float32(1.0) - first), "keys")
+        assert np.array_equal(side.astype(bool), first > 0.5)
+        assert_bit_equal(ctx.forward(x, s), first, "third forward")
+        fast = ctx.forward(x, s, pkg.MODE_FAST)
+        assert_rel_close(fast, first, 1e-4, "fast mode on reordered rows")
     finally:
         _setenv(**old)

@@ -19,7 +19,10 @@
 // EXACT=true keeps the reference's fp32 operation order (one accumulator per
 // output, k ascending, product and sum rounded separately, sequential
 // neighbour sums; see oracle/gnn_oracle.c) -> bit-identical scores.
-// EXACT=false contracts to FFMA and uses the device expf.
+// EXACT=false runs the dense layers on the tensor cores (mma.sync m16n8k8, 3 x TF32) and uses the device expf.
+// Both keep every bit the reference computes or stay within 1e-4 of it; the exact dense chain leaves out the
+// k steps whose activation is zero for the whole tile (tile_linear_relu), the exact sums of the largest
+// vertices are computed in parallel (gvc_px.cuh).
 //
 // Scheduling.  Real graphs are skewed (the R-MAT benchmark graph: 40 % isolated
 // vertices, 80 % of the adjacency in vertices of degree >= 64, one vertex of

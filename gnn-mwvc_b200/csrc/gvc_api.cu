@@ -510,7 +510,11 @@ int launch_stage(gvc_ctx *c, const float *d_in, float *d_out, float scale, int m
     // ms per stage): no window 1.77 / 4.24 / 4.00; 48 MB 1.78 / 4.14 / 3.90; 64 MB 1.84 / 4.10 / 3.90; 80 MB 1.92 /
     // 4.09 / 3.96 -- the set-aside is taken from everybody else's L2, stage 0 included, so more is not better.
     // GVC_L2_WINDOW_MB overrides the size (0 = off).
-    const bool wants_window = STAGE >= 1 && c->relabelled && (size_t)c->n_global * 64 > (size_t)(96u << 20);
+    static const size_t window_min_rows_bytes = [] {                    // GVC_L2_WINDOW_MIN_MB: rows of at least this size get the window
+        const char *e = std::getenv("GVC_L2_WINDOW_MIN_MB");
+        return e ? (size_t)std::strtoull(e, nullptr, 10) << 20 : (size_t)96 << 20;
+    }();
+    const bool wants_window = STAGE >= 1 && c->relabelled && (size_t)c->n_global * 64 > window_min_rows_bytes;
     const size_t l2_window = wants_window ? l2_window_bytes(c) : 0;     // the device limit is only touched for such graphs
     const bool windowed = l2_window != 0;
     if (windowed) {

@@ -67,3 +67,16 @@ def test_fails_loudly_without_gpu(lib):
 
 def test_abi_version(lib):
     assert lib.gvc_abi_version() == 4
+
+
+def test_every_environment_switch_is_documented():
+    """Each GVC_* variable the product reads (libgvc and the drop-in host units) is explained in INTEGRATION.md."""
+    pkg = ROOT / "gnn-mwvc_b200"
+    read = set()
+    for p in list((pkg / "csrc").glob("*")) + list((pkg / "host").glob("*.?pp")):
+        if p.is_file():
+            read |= set(re.findall(r'getenv\("(GVC_[A-Z0-9_]+)"\)', p.read_text()))
+    assert len(read) >= 10
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    missing = sorted(v for v in read if v not in doc)
+    assert not missing, missing
